@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.json by EXECUTING THE UNMODIFIED REFERENCE (/root/reference).
+
+Run in the build container only:   python oracle/gen_golden.py
+The fixtures pin the C oracle (oracle/splendor_oracle.c) and, through it, the CUDA path.  They are
+produced exclusively with reference code + CPython's `random` + numpy's PCG64 -- nothing from this
+repository's engine is involved in computing an expected value.
+
+Files written:
+  mt19937.json        CPython random.Random(seed) raw 32-bit outputs (seeds incl. >32-bit ones)
+  token_return.json   sha256 of the top-3-bit streams of all 8,910 in-domain auto_return_tokens seeds
+  initial_states.json initial_state(seed) flat rows + obs sha (incl. the SURVEY.md section 8c fingerprints)
+  env_seeding.json    SplendorEnv.reset(seed) -> engine seed / board (gymnasium PCG64 path)
+  games.json          full games under 3 deterministic policies: actions + per-step digest of
+                      (obs, mask, state row, reward, terminated, info bits) + a few full vectors
+  edge_cases.json     hand-built states mirroring the reference's own tests (tests/utils.py style
+                      mutation of env.state): full input row, action, and every output
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import random
+import struct
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import pyref  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+ns = pyref.load()
+R, ENC, ST, ENV = ns.rules, ns.encode, ns.state, ns.env
+
+
+def info_bits(info: dict, state) -> int:
+    b = 0
+    if info.get("illegal_action"):
+        b |= 1
+    if info.get("draw"):
+        b |= 2
+    if info.get("turn_limit"):
+        b |= 4
+    if R.is_terminal(state):
+        b |= 8
+        if "final_rewards" in info:
+            w = state.winner_index
+            b |= (0 if w is None else w + 1) << 4
+    return b
+
+
+def digest(obs, mask, row, reward, term, bits) -> str:
+    h = hashlib.sha256()
+    h.update(np.asarray(obs, np.int32).tobytes())
+    h.update(np.asarray(mask, np.int8).tobytes())
+    h.update(np.asarray(row, np.int32).tobytes())
+    h.update(struct.pack("<fBB", float(reward), int(bool(term)), bits))
+    return h.hexdigest()[:12]
+
+
+def env_from_state(state):
+    env = ENV.SplendorEnv()
+    env.reset(seed=0)
+    env.state = state
+    return env
+
+
+def dump(name, obj):
+    path = os.path.join(OUT, name)
+    with open(path, "w") as f:
+        json.dump(obj, f, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+# ----------------------------------------------------------------------------- mt19937.json
+def gen_mt():
+    seeds = [0, 1, 42, 19650218, 2**31 - 2, 2**32 - 1, 2**32, 2**32 + 1, (99 * 1315423911) ^ 2654435761 ^ (13 * 97531) ^ (14 * 31337),
+             2**40 + 7, 2**63 + 11]
+    out = []
+    for s in seeds:
+        r = random.Random(s)
+        outs = [r.getrandbits(32) for _ in range(1000)]  # crosses the 624-word regeneration boundary
+        out.append({"seed": str(s), "first": outs[:8], "sha_1000": hashlib.sha256(struct.pack("<1000I", *outs)).hexdigest()})
+    dump("mt19937.json", out)
+
+
+# ----------------------------------------------------------------------------- token_return.json
+def gen_token_return():
+    """auto_return_tokens seed domain in legitimate play (engine/rules.py:160-165): turn_count 1..99,
+    to_play 0..1, hand sum 11..13, bank sum 0..14.  getrandbits(k<=3) only uses the top 3 bits of each
+    32-bit output; 21 outputs are stored per seed."""
+    h = hashlib.sha256()
+    samples = {}
+    for turn in range(1, 100):
+        for tp in range(2):
+            for hand in range(11, 14):
+                for bank in range(0, 15):
+                    seed = (turn * 1315423911) ^ (tp * 2654435761) ^ (hand * 97531) ^ (bank * 31337)
+                    r = random.Random(seed)
+                    v = 0
+                    for j in range(21):
+                        v |= (r.getrandbits(32) >> 29) << (3 * j)
+                    h.update(struct.pack("<Q", v))
+                    if (turn, tp, hand, bank) in ((1, 0, 11, 0), (7, 1, 12, 9), (50, 0, 13, 14), (99, 1, 13, 14)):
+                        samples[f"{turn},{tp},{hand},{bank}"] = str(v)
+    dump("token_return.json", {"order": "turn,to_play,hand,bank (bank fastest)", "sha256": h.hexdigest(), "samples": samples})
+
+
+# ----------------------------------------------------------------------------- initial_states.json
+def gen_initial():
+    out = []
+    for seed in [0, 42, 123456789, 1, 2, 3, 7, 999, 2**31 - 2, 1826701614, 191664963, 33158374]:
+        s = R.initial_state(seed=seed)
+        obs = ENC.encode_observation(s)
+        out.append({"seed": seed, "row": pyref.state_to_row(s).tolist(),
+                    "obs_sha16": hashlib.sha256(obs.tobytes()).hexdigest()[:16],
+                    "mask": R.legal_moves(s)})
+    dump("initial_states.json", out)
+
+
+# ----------------------------------------------------------------------------- env_seeding.json
+def gen_env_seeding():
+    out = []
+    for seed in [0, 42, 123, 7]:
+        env = ENV.SplendorEnv()
+        obs, info = env.reset(seed=seed)
+        eng = int(np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed))).integers(0, 2**31 - 1))
+        assert np.array_equal(pyref.state_to_row(env.state), pyref.state_to_row(R.initial_state(seed=eng)))
+        # a second, unseeded reset keeps drawing from the same stream (ppo_splendor.py:246-247)
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        e1 = int(g.integers(0, 2**31 - 1))
+        e2 = int(g.integers(0, 2**31 - 1))
+        env.reset()
+        assert np.array_equal(pyref.state_to_row(env.state), pyref.state_to_row(R.initial_state(seed=e2)))
+        out.append({"seed": seed, "engine_seed": e1, "engine_seed_2nd_reset": e2,
+                    "gymnasium": ns.gymnasium, "numpy": np.__version__,
+                    "tier1_board": [c.id for c in R.initial_state(seed=e1).board[1]]})
+    dump("env_seeding.json", out)
+
+
+# ----------------------------------------------------------------------------- games.json
+def play(seed: int, policy: str):
+    state = R.initial_state(seed=seed)
+    env = env_from_state(state)
+    x = (seed * 2654435761) % 2**32
+    actions, digests, full = [], [], {}
+    t = 0
+    while True:
+        mask = R.legal_moves(env.state)
+        legal = [i for i, v in enumerate(mask) if v]
+        x = (1664525 * x + 1013904223) % 2**32
+        if not legal:
+            a = 0
+        elif policy == "first":
+            a = legal[0]
+        elif policy == "lcg":
+            a = legal[(x >> 16) % len(legal)]
+        elif policy == "lcg_illegal":
+            a = (x >> 8) % 45 if t % 7 == 3 else legal[(x >> 16) % len(legal)]
+        else:
+            raise ValueError(policy)
+        obs, r, term, trunc, info = env.step(a)
+        row = pyref.state_to_row(env.state)
+        bits = info_bits(info, env.state)
+        actions.append(a)
+        digests.append(digest(obs, info["action_mask"], row, r, term, bits))
+        if t in (0, 10, 40) or term:
+            full[str(t)] = {"obs": obs.tolist(), "mask": info["action_mask"].tolist(), "row": row.tolist(),
+                            "reward": float(r), "terminated": bool(term), "info": bits}
+        t += 1
+        if term or t >= 400:
+            break
+    s = env.state
+    return {"seed": seed, "policy": policy, "actions": actions, "digests": digests, "full": full,
+            "moves": s.move_count, "winner": s.winner_index, "prestige": [p.prestige for p in s.players]}
+
+
+def gen_games():
+    games = []
+    for seed in (0, 1, 999):
+        games.append(play(seed, "first"))
+        games.append(play(seed, "lcg"))
+    for seed in range(100, 118):
+        games.append(play(seed, "lcg"))
+    for seed in range(200, 212):
+        games.append(play(seed, "lcg_illegal"))
+    # SURVEY.md section 8c fingerprints (first-legal / LCG policies): moves, winner, prestige
+    g = {(x["seed"], x["policy"]): x for x in games}
+    assert (g[(0, "first")]["moves"], g[(0, "first")]["winner"], g[(0, "first")]["prestige"]) == (116, 0, [17, 16])
+    assert (g[(1, "lcg")]["moves"], g[(1, "lcg")]["winner"], g[(1, "lcg")]["prestige"]) == (62, 1, [6, 17])
+    dump("games.json", games)
+
+
+# ----------------------------------------------------------------------------- edge_cases.json
+def record(name, state, action, cite):
+    """Run SplendorEnv.step on a (possibly hand-mutated) state; store input row and every output."""
+    env = env_from_state(state)
+    row_in = pyref.state_to_row(env.state)
+    mask_in = R.legal_moves(env.state)
+    try:
+        obs, r, term, trunc, info = env.step(action)
+    except (RuntimeError, ValueError) as e:
+        return {"name": name, "cite": cite, "row_in": row_in.tolist(), "mask_in": mask_in, "action": action,
+                "raises": type(e).__name__}
+    return {"name": name, "cite": cite, "row_in": row_in.tolist(), "mask_in": mask_in, "action": action,
+            "row_out": pyref.state_to_row(env.state).tolist(), "obs": obs.tolist(),
+            "mask": info["action_mask"].tolist(), "reward": float(r), "terminated": bool(term),
+            "info": info_bits(info, env.state),
+            "final_rewards": [info["final_rewards"][0], info["final_rewards"][1]] if "final_rewards" in info else None}
+
+
+def cards_by_id():
+    c = ST._load_cards_from_json()
+    return {x.id: x for t in (1, 2, 3) for x in c[t]}
+
+
+def gen_edges():
+    C = cards_by_id()
+    out = []
+
+    # tests/test_rules.py:37-43 -- out-of-domain hand [5,5,5,5,5,0] then any action -> return to 10
+    s = R.initial_state(seed=0)
+    s.players[0].tokens = [5, 5, 5, 5, 5, 0]
+    out.append(record("token_limit_25_tokens", s, 0, "tests/test_rules.py:37-43"))
+    # tests/test_afford_nobles_obs.py:58-71 -- hand [3,3,3,3,3,0]
+    s = R.initial_state(seed=int(np.random.Generator(np.random.PCG64(np.random.SeedSequence(7))).integers(0, 2**31 - 1)))
+    s.players[0].tokens = [3, 3, 3, 3, 3, 0]
+    out.append(record("token_return_15_tokens", s, [i for i, v in enumerate(R.legal_moves(s)) if v][0],
+                      "tests/test_afford_nobles_obs.py:58-71"))
+    # gold-only overflow: hand of 9 gold + 2 white, take 3 -> must give back non-gold first then gold
+    s = R.initial_state(seed=5)
+    s.players[0].tokens = [0, 0, 0, 0, 0, 10]
+    out.append(record("token_return_gold_last_resort", s, 0, "engine/rules.py:169-184"))
+    # tests/test_draw_rule.py:7-24
+    s = R.initial_state(seed=0)
+    s.bank[:] = [0, 0, 0, 0, 0, 0]
+    s.players[0].tokens[:] = [10, 0, 0, 0, 0, 0]
+    s.players[0].reserved = s.decks[1][:3]
+    s.players[0].revealed_reserved = [True, True, True]
+    for t in (1, 2, 3):
+        s.board[t] = [None, None, None, None]
+    out.append(record("no_legal_move_draw", s, 0, "tests/test_draw_rule.py:7-24; envs/splendor_env.py:55-61"))
+    # same, but on player 1's turn with game_over already set by player 0 (state forced)
+    s = R.initial_state(seed=3)
+    s = R.apply_action(s, 0)
+    s.bank[:] = [0, 0, 0, 0, 0, 0]
+    s.players[1].tokens[:] = [0, 0, 0, 0, 0, 0]
+    s.players[1].reserved = s.decks[2][:3]
+    s.players[1].revealed_reserved = [False, True, False]
+    for t in (1, 2, 3):
+        s.board[t] = [None, None, None, None]
+    out.append(record("no_legal_move_draw_p1", s, 7, "envs/splendor_env.py:55-61"))
+    # tests/test_take_reduced_colors.py:7-21 and :24-36
+    s = R.initial_state(seed=123)
+    s.bank[:] = [1, 0, 2, 0, 0, 0]
+    out.append(record("take3_two_colours", s, 0, "tests/test_take_reduced_colors.py:7-21"))
+    s = R.initial_state(seed=123)
+    s.bank[:] = [1, 0, 2, 0, 0, 0]
+    out.append(record("take3_two_colours_illegal_combo", s, 1, "tests/test_take_reduced_colors.py:7-21"))
+    s = R.initial_state(seed=123)
+    s.bank[:] = [0, 0, 0, 0, 3, 0]
+    out.append(record("take3_one_colour", s, 2, "tests/test_take_reduced_colors.py:24-36"))
+    # tests/test_afford_nobles_obs.py:31-43 -- all bonuses 4: exactly one noble even on a take action
+    s = R.initial_state(seed=999)
+    s.players[0].bonuses = [4, 4, 4, 4, 4]
+    out.append(record("one_noble_per_turn", s, [i for i, v in enumerate(R.legal_moves(s)) if v][0],
+                      "tests/test_afford_nobles_obs.py:31-43; engine/rules.py:132-147"))
+    # tests/test_afford_nobles_obs.py:9-28 restated with a real card: discounts + gold substitution
+    s = R.initial_state(seed=123)
+    s.board[1][0] = C[2]  # cost white2 blue2 red1, colour black
+    s.players[0].tokens = [1, 2, 0, 0, 0, 2]
+    s.players[0].bonuses = [0, 0, 0, 0, 0]
+    out.append(record("buy_with_gold_substitution", s, 15, "tests/test_afford_nobles_obs.py:9-28; engine/rules.py:101-122"))
+    s = R.initial_state(seed=123)
+    s.board[1][0] = C[2]
+    s.players[0].tokens = [1, 2, 0, 0, 0, 1]
+    out.append(record("buy_unaffordable_is_illegal", s, 15, "tests/test_gym_compat.py:111-124; envs/splendor_env.py:64-66"))
+    s = R.initial_state(seed=123)
+    s.board[3][2] = C[89]  # green7 red3
+    s.players[0].tokens = [0, 0, 1, 0, 0, 3]
+    s.players[0].bonuses = [0, 0, 4, 2, 9]
+    out.append(record("buy_tier3_bonus_discount", s, 15 + 8 + 2, "engine/state.py:61-71"))
+    # reserve visible / blind, gold exhausted, 3rd reservation
+    s = R.initial_state(seed=11)
+    s.bank[5] = 0
+    out.append(record("reserve_visible_no_gold", s, 27 + 5, "engine/rules.py:226-240"))
+    s = R.initial_state(seed=11)
+    out.append(record("reserve_blind_tier3", s, 41, "engine/rules.py:241-249"))
+    s = R.initial_state(seed=11)
+    s.decks[3].clear()
+    out.append(record("reserve_blind_empty_deck_illegal", s, 41, "engine/rules.py:83-86"))
+    s = R.initial_state(seed=11)
+    s.decks[2].clear()
+    out.append(record("buy_visible_no_refill", s, 15 + 4, "engine/rules.py:125-129"))
+    s = R.initial_state(seed=11)
+    s.decks[2].clear()
+    s.players[0].tokens = [3, 3, 3, 3, 3, 2]
+    s.players[0].bonuses = [3, 3, 3, 3, 3]
+    out.append(record("buy_visible_empty_deck_leaves_hole", s, 15 + 4, "engine/rules.py:125-129,216-225"))
+    # buy reserved: list.pop(idx) shifts ([33,35,37] -> [35,37])
+    s = R.initial_state(seed=21)
+    s.players[0].reserved = [C[33], C[35], C[37]]
+    s.players[0].revealed_reserved = [True, False, True]
+    s.players[0].tokens = [2, 2, 2, 2, 2, 0]
+    s.players[0].bonuses = [2, 2, 2, 2, 2]
+    out.append(record("buy_reserved_slot0_shifts", s, 42, "engine/rules.py:250-255"))
+    s = R.initial_state(seed=21)
+    s.players[0].reserved = [C[33], C[35], C[37]]
+    s.players[0].revealed_reserved = [True, False, True]
+    s.players[0].tokens = [2, 2, 2, 2, 2, 0]
+    s.players[0].bonuses = [2, 2, 2, 2, 2]
+    out.append(record("buy_reserved_slot1_shifts", s, 43, "engine/rules.py:250-255"))
+    # opponent's hidden reservation is 14 zeros in the observation (tests/test_reserved_card_observation.py:112-138)
+    s = R.initial_state(seed=31)
+    s = R.apply_action(s, 39)   # P0 reserves blind tier 1
+    s = R.apply_action(s, 27)   # P1 reserves visible
+    out.append(record("opponent_hidden_reserved_obs", s, 40, "tests/test_reserved_card_observation.py:112-138"))
+    # end of game: P0 reaches 15 -> game_over but not terminal; P1's reply terminates
+    s = R.initial_state(seed=41)
+    s.players[0].prestige = 14
+    s.players[0].bonuses = [7, 7, 7, 7, 7]
+    s.board[1][0] = C[7]  # 1 point
+    st_mid = record("p0_reaches_15_not_terminal", s, 15, "engine/rules.py:263-285")
+    out.append(st_mid)
+    s2 = pyref.row_to_state(st_mid["row_out"])
+    out.append(record("p1_last_move_terminal_p0_wins", s2, 0, "envs/splendor_env.py:68-88"))
+    # P1 reaches 15 first: immediate terminal, mover wins -> +1
+    s = R.initial_state(seed=41)
+    s = R.apply_action(s, 0)
+    s.players[1].prestige = 14
+    s.players[1].bonuses = [7, 7, 7, 7, 7]
+    s.board[1][1] = C[7]
+    out.append(record("p1_reaches_15_wins", s, 16, "engine/rules.py:282-285"))
+    # tie-breaks: equal prestige, fewer cards wins; exact tie -> None
+    for name, b0, b1, r0 in (("tiebreak_fewer_cards", [3, 3, 3, 3, 3], [2, 3, 3, 3, 3], 0), ("tiebreak_exact_tie", [3, 3, 3, 3, 3], [3, 3, 3, 3, 3], 0),
+                             ("tiebreak_fewer_reserved", [3, 3, 3, 3, 3], [3, 3, 3, 3, 3], 1)):
+        s = R.initial_state(seed=51)
+        s = R.apply_action(s, 0)
+        s.game_over = True
+        s.players[0].prestige = 16
+        s.players[1].prestige = 16
+        s.players[0].bonuses = list(b0)
+        s.players[1].bonuses = list(b1)
+        if r0:
+            s.players[0].reserved = [C[50]]
+            s.players[0].revealed_reserved = [True]
+        out.append(record(name, s, 1, "engine/rules.py:290-303"))
+    # turn limit: move 198 -> draw by limit overrides a real win
+    s = R.initial_state(seed=61)
+    s.move_count = 197
+    s.turn_count = 99
+    s.to_play = 1
+    s.players[1].prestige = 20
+    out.append(record("turn_limit_overrides_win", s, 0, "engine/rules.py:274-279; envs/splendor_env.py:71-75"))
+    s = R.initial_state(seed=61)
+    s.move_count = 196
+    s.turn_count = 99
+    s.to_play = 0
+    out.append(record("move_197_not_terminal", s, 0, "engine/rules.py:268-279"))
+    # step after termination raises (tests/test_gym_compat.py:89-108); out-of-range action raises
+    s = R.initial_state(seed=61)
+    s.game_over = True
+    out.append(record("step_after_terminal", s, 0, "envs/splendor_env.py:53-54"))
+    s = R.initial_state(seed=61)
+    out.append(record("action_out_of_range", s, 45, "envs/splendor_env.py:62-63"))
+    s = R.initial_state(seed=61)
+    out.append(record("action_negative", s, -1, "envs/splendor_env.py:62-63"))
+    # take-2 needs 4 (tests/test_rules.py:29-34)
+    s = R.initial_state(seed=71)
+    s.bank[2] = 3
+    out.append(record("take2_needs_four_illegal", s, 12, "tests/test_rules.py:29-34"))
+    s = R.initial_state(seed=71)
+    out.append(record("take2_ok", s, 12, "engine/rules.py:211-215"))
+    # in-domain token return with k=1,2,3 (hand 10 + take 3 / take 2 / reserve with gold)
+    s = R.initial_state(seed=81)
+    s.players[0].tokens = [2, 2, 2, 2, 2, 0]
+    s.bank[:] = [2, 2, 2, 2, 2, 5]
+    out.append(record("return_k3", s, 4, "engine/rules.py:150-193"))
+    s = R.initial_state(seed=81)
+    s.players[0].tokens = [0, 0, 3, 3, 3, 1]
+    s.bank[:] = [4, 4, 1, 1, 1, 4]
+    out.append(record("return_k2_take2", s, 10, "engine/rules.py:150-193"))
+    s = R.initial_state(seed=81)
+    s.players[0].tokens = [5, 0, 0, 0, 0, 5]
+    out.append(record("return_k1_reserve_gold", s, 27, "engine/rules.py:150-193,236-239"))
+    dump("edge_cases.json", out)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_mt()
+    gen_token_return()
+    gen_initial()
+    gen_env_seeding()
+    gen_games()
+    gen_edges()
