@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the hot path (legality check + step + legal mask + observation encode +
+same-step auto-reset) on N B200s, with the roofline of the dominant kernel, a CPU baseline, and the
+end-to-end number through the public API with host buffers.
+
+Workload (BASELINE.json configs[1]): 2-player random-legal-policy lock-step rollout, 65,536 envs per GPU.
+One bench "step" = one rollout segment: ROLLOUT lock-steps of all envs, each writing its observations /
+masks / rewards / terminations / actions into a [ROLLOUT, N, ...] rollout buffer (what ppo_splendor.py's
+obs_buf/masks_buf/... hold, ppo_splendor.py:210-297), replayed as one CUDA graph.  The rollout buffer
+(10.4 GB at the defaults) is far larger than the 126 MB L2, so no L2 flush is needed between iterations.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--rollout T] [--impl reference]
+  torchrun ... bench.py --gpus N ...      (one rank per GPU; env shards are independent, weak scaling)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_FULL = 1370  # algorithmic bytes per env-step: obs 1188 + mask 45 + reward 4 + term 1 + action 4 + state 64 r + 64 w
+B_MASKSTEP = 182
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--rollout", type=int, default=128, help="lock-steps per bench step (ppo_splendor.py --num-steps)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-obs", action="store_true", help="config 4: mask + step only (no observation encode)")
+    ap.add_argument("--shuffle", default="philox", choices=["philox", "mt19937"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------- CPU legs
+def cpu_rollout(envs: int, seconds: float, threads: int | None = None):
+    """Oracle port of the reference engine on the host cores: random-legal lock-step rollout with same-step
+    auto-reset, full step+mask+obs per env-step. Returns (steps_per_s, threads, description)."""
+    from oracle import oracle as O
+
+    O.build()
+    if threads:
+        O.set_num_threads(threads)
+    nthreads = O.num_threads()
+    v = O.OracleVec(envs, seed_base=0)
+    v.reset()
+    v.rollout_random(0xB200, 0, 2)  # warm-up
+    t0 = time.perf_counter()
+    done, T, chunk = 0, 2, 4
+    while True:
+        done += v.rollout_random(0xB200, T, chunk)
+        T += chunk
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return done / el, nthreads, f"{envs} envs x {T - 2} lock-steps ({done} env-steps, {el:.1f} s), C port of the reference engine (oracle/), OpenMP"
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host cores (oracle port; the Python reference
+    cannot travel to the GPU box), all threads, same workload/metric. Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import oracle as O
+
+    O.build()
+    nthreads = O.num_threads()
+    envs = args.envs
+    chunk = 8  # lock-steps per bench step: a bounded sample of the rollout segment
+    v = O.OracleVec(envs, seed_base=0)
+    v.reset()
+    T = 0
+    for _ in range(max(args.warmup, 1)):
+        v.rollout_random(0xB200, T, chunk)
+        T += chunk
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        done += v.rollout_random(0xB200, T, chunk)
+        T += chunk
+    el = time.perf_counter() - t0
+    val = done / el
+    sample = f"{envs} envs x {chunk} lock-steps per step (of the {args.rollout}-step segment), oracle C port, {nthreads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": f"2-player random-legal lock-step rollout, {envs} envs (BASELINE configs[1]) on host CPU",
+                   "envs": envs, "lock_steps_per_step": chunk},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    N, T, K, W = args.envs, args.rollout, args.steps, max(args.warmup, 3)
+    # cap the rollout buffer at ~40 GB
+    per_step_bytes = N * (1188 + 45 + 4 + 1 + 4)
+    T = max(1, min(T, int(40e9 // per_step_bytes)))
+    write_obs = not args.no_obs
+
+    env = SplendorVecEnv(N, device=dev, seed=20261018, shuffle=args.shuffle, env_offset=rank * N, autoreset=True)
+    obs_buf = torch.zeros((T, N, 297), dtype=torch.int32, device=dev) if write_obs else None
+    mask_buf = torch.zeros((T, N, 45), dtype=torch.int8, device=dev)
+    rew_buf = torch.zeros((T, N), dtype=torch.float32, device=dev)
+    term_buf = torch.zeros((T, N), dtype=torch.uint8, device=dev)
+    act_buf = torch.zeros((T + 1, N), dtype=torch.int32, device=dev)
+    env.t_base = torch.zeros(1, dtype=torch.int64, device=dev)
+    env.reset()
+    env.sample_random_actions(out=act_buf[0])
+
+    def segment():
+        """T lock-steps into the rollout buffer; the actions for step t+1 are sampled by step t's kernel."""
+        for t in range(T):
+            env._t = t
+            env.step(act_buf[t], out_obs=(obs_buf[t] if write_obs else None), out_mask=mask_buf[t], out_reward=rew_buf[t],
+                     out_terminated=term_buf[t], out_next_action=act_buf[t + 1], write_obs=write_obs)
+        act_buf[0].copy_(act_buf[T])
+        env.t_base += T
+
+    launches0 = lib.spl_launch_count()
+    segment()  # eager once (also validates arguments)
+    torch.cuda.synchronize()
+    launches_per_segment = lib.spl_launch_count() - launches0
+    graph = None
+    if not args.no_graph:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            segment()
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            segment()
+    run = graph.replay if graph is not None else segment
+
+    stats_host = torch.zeros(8, dtype=torch.int64, device=dev)
+    for _ in range(W):
+        run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        run()
+        if world > 1:  # episode statistics are the only cross-GPU traffic (NCCL all-reduce of 8 int64)
+            stats_host.copy_(env.stats)
+            dist.all_reduce(stats_host)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    total_steps = N * T * K * world
+    value = total_steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: CUDA events recorded by the library around every step-kernel launch
+    peak, peak_src = peaks()
+    L.check(lib.spl_timing_enable(1))
+    reps = max(1, min(K, 4096 // T))
+    for _ in range(reps):
+        segment()
+    import ctypes as C
+
+    tot, cnt = C.c_double(), C.c_int64()
+    L.check(lib.spl_timing_read(C.byref(tot), C.byref(cnt)))
+    L.check(lib.spl_timing_enable(0))
+    bytes_per_unit = B_FULL if write_obs else B_MASKSTEP
+    k_ms = tot.value / max(1, cnt.value)
+    achieved = N * bytes_per_unit / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "spl_step_kernel<true>", "kernel_ms": k_ms, "launches_timed": cnt.value,
+                "algorithmic_bytes_per_env_step": bytes_per_unit, "peak_source": peak_src}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                tj = json.load(f)
+            key = f"{N}"
+            if key in tj:
+                roofline["traffic"] = tj[key]["dram_bytes_per_launch"]
+                roofline["traffic_source"] = tj[key].get("source")
+        except Exception:
+            pass
+
+    # ---- end-to-end through the public API with HOST buffers (H2D actions, D2H everything the reference's step returns)
+    e2e = None
+    if not args.skip_e2e:
+        env2 = env
+        h_act = torch.zeros(N, dtype=torch.int32).pin_memory()
+        h_obs = torch.zeros((N, 297), dtype=torch.int32).pin_memory()
+        h_mask = torch.zeros((N, 45), dtype=torch.int8).pin_memory()
+        h_rew = torch.zeros(N, dtype=torch.float32).pin_memory()
+        h_term = torch.zeros(N, dtype=torch.uint8).pin_memory()
+        h_next = torch.zeros(N, dtype=torch.int32).pin_memory()
+        d_act = torch.zeros(N, dtype=torch.int32, device=dev)
+        h_act.copy_(act_buf[0])
+        torch.cuda.synchronize()
+        n_e2e = max(20, min(200, 4 * T))
+
+        def host_step():
+            d_act.copy_(h_act, non_blocking=True)
+            obs, rew, term, _, info = env2.step(d_act, sample_next=True)
+            h_obs.copy_(obs, non_blocking=True)
+            h_mask.copy_(env2.mask, non_blocking=True)
+            h_rew.copy_(rew, non_blocking=True)
+            h_term.copy_(env2._terminated, non_blocking=True)
+            h_next.copy_(env2.next_action, non_blocking=True)
+            torch.cuda.synchronize()
+            h_act.copy_(h_next)  # the host-side "policy": actions come back from host memory every step
+
+        for _ in range(5):
+            host_step()
+        if world > 1:
+            dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n_e2e):
+            host_step()
+        a1.record()
+        torch.cuda.synchronize()
+        ems = a0.elapsed_time(a1)
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": N * n_e2e * world / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N,
+               "d2h_bytes_per_step": N * (1188 + 45 + 4 + 1 + 4), "lock_steps": n_e2e,
+               "api": "SplendorVecEnv.step(actions) with pinned host actions in, obs/mask/reward/terminated/next-actions out to pinned host memory"}
+
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        v, cores, sample = cpu_rollout(min(N, 65536), args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if world > 1:
+        stats_host.copy_(env.stats)
+        dist.all_reduce(stats_host)
+    else:
+        stats_host.copy_(env.stats)
+    st = stats_host.cpu().tolist()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {
+                "workload": ("2-player random-legal lock-step rollout, %d envs per GPU (BASELINE configs[1]%s), step+mask+obs+same-step auto-reset"
+                             % (N, "" if N == 65536 else "; envs overridden")) if write_obs else
+                            "simplified take-3 rules, mask+step only (BASELINE configs[3]), %d envs per GPU" % N,
+                "envs_per_gpu": N, "lock_steps_per_step": T, "env_steps_per_step": N * T * world, "shuffle": args.shuffle,
+                "cuda_graph": graph is not None, "parallelism": f"env-sharded x{world}, no collective on the step path",
+                "l2": "rollout buffer %.1f GB per GPU is larger than the 126 MB L2; no flush" % (T * per_step_bytes / 1e9),
+            },
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches_per_segment * K), "clocks": clocks,
+            "episode_stats": dict(zip(L.STAT_NAMES, st)),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,167 @@
+/*
+ * splendor_b200.h -- C ABI of the B200-native batched Splendor engine (libsplendor_b200.so).
+ *
+ * The reference (YiyangShao/splendor-gym) is pure Python and has no FFI layer; the boundary this
+ * library replaces is the pair of Python APIs
+ *     splendor_gym/envs/splendor_env.py:41-90   SplendorEnv.reset / SplendorEnv.step
+ *     splendor_gym/engine/rules.py:40-93,196-287 legal_moves / apply_action
+ *     splendor_gym/engine/encode.py:124-187      encode_observation
+ * evaluated for N independent environments in lock-step (what gym.vector.SyncVectorEnv and the
+ * per-env loop of ppo_splendor.py:235-250 do serially).  Each entry point below names the
+ * reference interface it stands in for.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates; the library keeps
+ *    only per-device constant tables);  all work is enqueued on `stream` and is asynchronous;
+ *  - return value 0 = ok, >0 = cudaError_t, <0 = SPL_E_* argument error; nothing throws or exits;
+ *  - functions are re-entrant for disjoint buffers; one CUDA device per process is assumed.
+ */
+#ifndef SPLENDOR_B200_H
+#define SPLENDOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPL_NUM_ACTIONS 45 /* engine/encode.py:32 TOTAL_ACTIONS */
+#define SPL_OBS_DIM 297    /* engine/encode.py:74 OBSERVATION_DIM */
+#define SPL_ROW_LEN 166    /* flat int32 debug row, see SPL_ROW_* below */
+#define SPL_STATE_PLANES 4 /* packed hot state: 4 planes of 16 B per env = 64 B */
+#define SPL_DECK_STRIDE 96 /* bytes per env of deck order (90 used: tier1[40] tier2[30] tier3[20]) */
+#define SPL_RET_TABLE_LEN 8910
+
+/* info byte written per env by spl_step (envs/splendor_env.py:56-88 info dict, flattened) */
+#define SPL_INFO_ILLEGAL 1u      /* info["illegal_action"]: reward -0.01, state unchanged (:64-66) */
+#define SPL_INFO_NOLEGAL_DRAW 2u /* info["draw"]: no legal move -> draw (:55-61) */
+#define SPL_INFO_TURN_LIMIT 4u   /* info["turn_limit"] (:84-85) */
+#define SPL_INFO_TERMINATED 8u
+#define SPL_INFO_WINNER_SHIFT 4 /* bits 4-5: 0 = None, 1 = player 0, 2 = player 1 (final_rewards derive from it) */
+#define SPL_INFO_WINNER_MASK 0x30u
+#define SPL_INFO_ERROR 64u /* the reference would raise: action out of range (ValueError :62-63) or, with
+                              TERMINATED also set, step after termination (RuntimeError :53-54); state unchanged */
+#define SPL_INFO_RESET 128u /* same-step auto-reset happened: obs/mask belong to the new episode */
+
+/* deck shuffles at reset (engine/state.py:181-195) */
+#define SPL_SHUFFLE_MT19937 0 /* bit-exact with initial_state(seed): CPython random.Random(seed).shuffle */
+#define SPL_SHUFFLE_PHILOX 1  /* native counter-based stream (distribution-equivalent, not bit-equal) */
+
+/* stats[8] accumulated (int64 atomics) per finished episode */
+#define SPL_STAT_EPISODES 0
+#define SPL_STAT_P0_WINS 1
+#define SPL_STAT_P1_WINS 2
+#define SPL_STAT_TIE_DRAWS 3
+#define SPL_STAT_LIMIT_DRAWS 4
+#define SPL_STAT_NOLEGAL_DRAWS 5
+#define SPL_STAT_SUM_MOVES 6
+#define SPL_STAT_SUM_WINNER_PRESTIGE 7
+
+#define SPL_E_BADARG (-1)
+#define SPL_E_NOTINIT (-2)
+#define SPL_E_ALIGN (-3)
+
+/* Flat int32 state row (export/import, parity checks): mirrors the reference dataclasses
+ * (engine/state.py:52-87) field by field; -1 = None / absent.
+ *   [0:6] bank | player p at 6+23p: [+0:6] tokens [+6:11] bonuses [+11] prestige [+12] len(reserved)
+ *   [+13:16] reserved card ids [+16:19] revealed flags [+19] len(nobles) [+20:23] noble indices |
+ *   [52:64] board ids tier-major | [64:67] deck sizes | [67:70] visible nobles | [70] to_play
+ *   [71] turn_count [72] move_count [73] game_over [74] winner_index [75] turn_limit_reached
+ *   [76:116] deck tier 1, [116:146] tier 2, [146:166] tier 3 (bottom..top, -1 beyond the size) */
+#define SPL_ROW_BANK 0
+#define SPL_ROW_PLAYER0 6
+#define SPL_ROW_PLAYER_STRIDE 23
+#define SPL_ROW_BOARD 52
+#define SPL_ROW_DECK_SIZES 64
+#define SPL_ROW_NOBLES 67
+#define SPL_ROW_TO_PLAY 70
+#define SPL_ROW_TURN_COUNT 71
+#define SPL_ROW_MOVE_COUNT 72
+#define SPL_ROW_GAME_OVER 73
+#define SPL_ROW_WINNER 74
+#define SPL_ROW_TURN_LIMIT 75
+#define SPL_ROW_DECK1 76
+#define SPL_ROW_DECK2 116
+#define SPL_ROW_DECK3 146
+
+/* The environments of one shard: structure-of-arrays game state in HBM (replaces the per-env
+ * SplendorState dataclass, engine/state.py:74-104). */
+typedef struct spl_envs {
+	void *state;         /* uint4[SPL_STATE_PLANES][stride]: packed 64-B hot rows, plane-major, 16-B aligned */
+	uint8_t *decks;      /* [n][SPL_DECK_STRIDE] deck order (cold; written at reset, 1 B read per refill) */
+	uint32_t *episode;   /* [n] episodes started per env (drives the per-episode seed schedule) */
+	int32_t *scratch;    /* [n + 4] work list of envs to auto-reset (library-internal use) */
+	int64_t stride;      /* envs per plane (>= n) */
+	int64_t n;           /* environments in this shard */
+	uint64_t env_offset; /* global id of env 0 (multi-GPU sharding: seeds depend on the global id only) */
+	uint64_t seed_base;  /* engine seed of (global env g, episode e) = (seed_base + 1000003 e + g) mod (2^31-1) */
+	int32_t shuffle_mode; /* SPL_SHUFFLE_* */
+	int32_t reserved_;
+} spl_envs_t;
+
+/* Outputs of one lock-step (the 5-tuple of SplendorEnv.step, batched). Nullable members are skipped. */
+typedef struct spl_step_io {
+	const int32_t *actions; /* [n] */
+	const uint8_t *active;  /* [n] nullable: 0 = leave this env untouched this call (dual_step phase 2) */
+	int32_t *obs;           /* [n][297] nullable */
+	int8_t *mask;           /* [n][45]  nullable: info["action_mask"] of the returned observation */
+	float *reward;          /* [n] */
+	uint8_t *terminated;    /* [n] */
+	uint8_t *info;          /* [n] SPL_INFO_* */
+	int64_t *stats;         /* [8] nullable */
+	int32_t *next_action;   /* [n] nullable: uniform random legal action for the returned mask (fused sampler) */
+	uint64_t action_key;    /* Philox key / lock-step counter for next_action */
+	uint64_t action_t;
+	const uint64_t *action_t_base; /* nullable device scalar added to action_t (lets a captured CUDA graph advance
+	                                  the sampler's counter between replays) */
+	int32_t autoreset; /* same-step auto-reset (ppo_splendor.py:245-250) */
+	int32_t reserved_;
+} spl_step_io_t;
+
+/* Upload the card / noble / token-return tables to the current device. Idempotent. */
+int spl_init(void);
+
+/* SplendorEnv.reset (envs/splendor_env.py:41-49) for every env, or those with reset_mask[i] != 0.
+ * Engine seeds: explicit `seeds[i]` if non-NULL, else the schedule above (episode[i] is zeroed on a
+ * full reset and incremented on a masked one).  Writes obs / mask if non-NULL. */
+int spl_reset(const spl_envs_t *envs, const uint64_t *seeds, const uint8_t *reset_mask, int32_t *obs, int8_t *mask,
+              void *stream);
+
+/* SplendorEnv.step (envs/splendor_env.py:51-90) for every env in lock-step:
+ * legality check -> apply_action -> encode_observation -> legal_moves [-> same-step auto-reset]. */
+int spl_step(const spl_envs_t *envs, const spl_step_io_t *io, void *stream);
+
+/* encode_observation (engine/encode.py:124-187) + legal_moves (engine/rules.py:40-93) of the current
+ * states, without stepping (mask is all-zero for terminal states, as in envs/splendor_env.py:81). */
+int spl_observe(const spl_envs_t *envs, int32_t *obs, int8_t *mask, void *stream);
+
+/* random_opponent (wrappers/selfplay.py:66-73) batched: uniform over the legal actions of mask[n][45],
+ * a = k-th set bit with k = philox4x32-10(key, ctr=(global env, t)).x mod popcount; 0 if none legal. */
+int spl_random_action(const int8_t *mask, int64_t n, uint64_t env_offset, uint64_t key, uint64_t t, int32_t *actions,
+                      void *stream);
+
+/* packed state <-> flat int32 rows [n][SPL_ROW_LEN] (device pointers). Import recomputes nothing else. */
+int spl_export_state(const spl_envs_t *envs, int32_t *rows, void *stream);
+int spl_import_state(const spl_envs_t *envs, const int32_t *rows, const uint8_t *which, void *stream);
+
+/* DualStepNativeWrapper.dual_step reward bookkeeping (wrappers/dual_step_native.py:132-167,195-201):
+ * combines phase-1 (agent) and phase-2 (opponent) step results into agent_reward / opp_reward / done. */
+int spl_dual_combine(const float *r1, const uint8_t *term1, const uint8_t *info1, const float *r2, const uint8_t *term2,
+                     const uint8_t *info2, int64_t n, float *agent_reward, float *opp_reward, uint8_t *done,
+                     void *stream);
+
+const char *spl_error_string(int code);
+int spl_version(void);
+/* host copy of the token-return table (SPL_RET_TABLE_LEN x u64) for tests */
+int spl_host_ret_table(uint64_t *out);
+/* number of kernels this library has launched since load (bench.py "gpu_launches") */
+int64_t spl_launch_count(void);
+/* measurement aid: when enabled, spl_step records CUDA events on the caller's stream around its main
+ * kernel; spl_timing_read synchronises and returns the summed duration [ms] and launch count */
+int spl_timing_enable(int on);
+int spl_timing_read(double *total_ms, int64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

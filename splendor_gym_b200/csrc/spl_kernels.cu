@@ -1,0 +1,798 @@
+// spl_kernels.cu -- sm_100a kernels + C ABI of the batched Splendor engine (include/splendor_b200.h).
+//
+// Execution model: one environment per lane, one warp per tile of 32 environments, persistent CTAs
+// looping over tiles.  The branchy integer rules run per lane on the packed 64-byte state
+// (spl_core.cuh); everything that touches HBM is warp-cooperative:
+//   * state   : 4 planes of uint4[N]  -> 4 fully coalesced LDG.128 / STG.128 per warp
+//   * obs     : each lane encodes its 297 entries as BYTES into a flat [32 x 297]-byte shared-memory
+//               tile (lane-dependent byte shift + neighbour shuffle so rows abut exactly); the warp then
+//               streams the tile out as 2376 int4 = 38,016 contiguous, 16-B aligned bytes of int32
+//   * mask    : 45-bit ballot-style bitset per lane, exchanged by shuffle and expanded to the contiguous
+//               [32 x 45] int8 tile as 90 int4 stores
+// No tensor cores: the path is integer/branch logic bounded by HBM writes (1,370 B per env-step).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "spl_core.cuh"
+#include "spl_tables_host.h"
+
+#define SPL_WARPS_PER_CTA 4
+#define SPL_TILE_WORDS 2376 /* 32 envs * 297 bytes / 4 */
+#define SPL_FULL 0xFFFFFFFFu
+#define SPL_DECK_SMEM 100 /* per-lane deck row in shared memory: 25 words (odd) to spread banks */
+
+__device__ SplTables g_tables;
+__device__ uint64_t g_ret_table[SPL_RET_TABLE_LEN];
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) -- counter-based stream for action sampling and native shuffles
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 spl_philox(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+	for (int r = 0; r < 10; r++) {
+		uint32_t h0 = __umulhi(0xD2511F53u, c.x), l0 = 0xD2511F53u * c.x;
+		uint32_t h1 = __umulhi(0xCD9E8D57u, c.z), l1 = 0xCD9E8D57u * c.z;
+		c = make_uint4(h1 ^ c.y ^ k0, l1, h0 ^ c.w ^ k1, l0);
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+	return c;
+}
+
+// index of the k-th (0-based) set bit of a 45-bit set
+__device__ __forceinline__ uint32_t spl_kth_set_bit(uint64_t m, uint32_t k) {
+	uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+	uint32_t nlo = __popc(lo);
+	uint32_t word = lo, base = 0;
+	if (k >= nlo) {
+		k -= nlo;
+		word = hi;
+		base = 32;
+	}
+#pragma unroll
+	for (int sh = 16; sh >= 1; sh >>= 1) {
+		uint32_t c = __popc(word & ((1u << sh) - 1u));
+		if (k >= c) {
+			k -= c;
+			word >>= sh;
+			base += sh;
+		}
+	}
+	return base;
+}
+
+__device__ __forceinline__ int32_t spl_sample_action(uint64_t m, uint64_t key, uint64_t genv, uint64_t t) {
+	uint32_t n = __popcll(m);
+	if (n == 0) return 0;  // wrappers/selfplay.py:66-73
+	uint4 r = spl_philox(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)t, (uint32_t)(t >> 32)),
+	                     (uint32_t)key, (uint32_t)(key >> 32));
+	return (int32_t)spl_kth_set_bit(m, r.x % n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-cooperative tile output
+// ------------------------------------------------------------------------------------------------
+// [32 x 45] int8 action-mask tile from one 45-bit set per lane.  `rows` = valid envs in the tile.
+__device__ __forceinline__ void spl_store_mask_tile(int8_t* gtile, uint64_t m, int lane, int rows) {
+	const int tile_bytes = rows * SPL_NUM_ACTIONS;
+#pragma unroll
+	for (int it = 0; it < 3; it++) {
+		int q = lane + 32 * it;  // int4 index, 90 per full tile
+		int byte0 = 16 * q;
+		int env_lo = byte0 / SPL_NUM_ACTIONS;
+		int a0 = byte0 - env_lo * SPL_NUM_ACTIONS;
+		uint64_t m_lo = __shfl_sync(SPL_FULL, m, env_lo & 31);
+		uint64_t m_hi = __shfl_sync(SPL_FULL, m, (env_lo + 1) & 31);
+		uint32_t bits = (uint32_t)((m_lo >> a0) | (m_hi << (SPL_NUM_ACTIONS - a0))) & 0xFFFFu;
+		int4 v;
+		v.x = (int)spl_spread4(bits);
+		v.y = (int)spl_spread4(bits >> 4);
+		v.z = (int)spl_spread4(bits >> 8);
+		v.w = (int)spl_spread4(bits >> 12);
+		if (byte0 + 16 <= tile_bytes) {
+			__stcs(reinterpret_cast<int4*>(gtile) + q, v);
+		} else if (byte0 < tile_bytes) {  // ragged last tile
+			const int8_t* b = reinterpret_cast<const int8_t*>(&v);
+			for (int j = 0; byte0 + j < tile_bytes; j++) gtile[byte0 + j] = b[j];
+		}
+	}
+}
+
+// Stage one lane's observation (75 words of bytes) into the flat byte tile.  Row r starts at byte 297 r,
+// i.e. word (297 r)>>2 with a byte shift of r&3; a lane writes exactly the tile words that START inside
+// its row, completing its last word with the first bytes of the next lane's row (= that lane's packed
+// word 0, fetched by shuffle).
+struct SplObsStager {
+	uint32_t* dst;
+	uint32_t shift8, prev, next_r0;
+	__device__ __forceinline__ SplObsStager(uint32_t* tile, int lane, uint32_t w0)
+	    : dst(tile + ((SPL_OBS_DIM * lane) >> 2)), shift8(8u * (lane & 3)), prev(0) {
+		next_r0 = __shfl_down_sync(SPL_FULL, w0, 1);
+	}
+	__device__ __forceinline__ void operator()(int k, uint32_t v) {
+		if (k == 74) v |= next_r0 << 8;
+		if (k == 0) {
+			if (shift8 == 0) dst[0] = v;
+		} else {
+			dst[k] = __funnelshift_l(prev, v, shift8);
+		}
+		prev = v;
+	}
+};
+
+// stream a staged tile to global memory as int32 (rows == 32: 2376 aligned int4; otherwise per entry)
+__device__ __forceinline__ void spl_store_obs_tile(int32_t* gtile, const uint32_t* tile, int lane, int rows, bool vec) {
+	if (rows == 32 && vec) {
+		int4* g4 = reinterpret_cast<int4*>(gtile);
+#pragma unroll 6
+		for (int q = lane; q < SPL_TILE_WORDS; q += 32) {
+			uint32_t v = tile[q];
+			int4 o = make_int4((int)(v & 0xFFu), (int)((v >> 8) & 0xFFu), (int)((v >> 16) & 0xFFu), (int)(v >> 24));
+			__stcs(g4 + q, o);
+		}
+	} else {
+		const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+		for (int e = lane; e < rows * SPL_OBS_DIM; e += 32) gtile[e] = (int32_t)tb[e];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// step / observe kernel
+// ------------------------------------------------------------------------------------------------
+struct StepParams {
+	uint4* state;
+	int64_t stride;
+	const uint8_t* decks;
+	int32_t* scratch;
+	int64_t n;
+	uint64_t env_offset;
+	const int32_t* actions;
+	const uint8_t* active;
+	int32_t* obs;
+	int8_t* mask;
+	float* reward;
+	uint8_t* terminated;
+	uint8_t* info;
+	unsigned long long* stats;
+	int32_t* next_action;
+	uint64_t action_key, action_t;
+	const uint64_t* action_t_base;
+	int autoreset;
+	int vec_ok;  // obs / mask bases are 16-byte aligned
+};
+
+template <bool DO_STEP>
+__global__ void __launch_bounds__(SPL_WARPS_PER_CTA * 32) spl_step_kernel(const StepParams p) {
+	__shared__ SplTables T;
+	__shared__ uint32_t tiles[SPL_WARPS_PER_CTA][SPL_TILE_WORDS];
+	{
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+		for (int i = threadIdx.x; i < (int)(sizeof(SplTables) / 4); i += blockDim.x) dst[i] = src[i];
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t* tile = tiles[warp];
+	const int64_t ntiles = (p.n + 31) >> 5;
+
+	for (int64_t ti = (int64_t)blockIdx.x * SPL_WARPS_PER_CTA + warp; ti < ntiles; ti += (int64_t)gridDim.x * SPL_WARPS_PER_CTA) {
+		const int64_t env = ti * 32 + lane;
+		const bool valid = env < p.n;
+		const int rows = (int)min((int64_t)32, p.n - ti * 32);
+		uint32_t w[16];
+		if (valid) {
+#pragma unroll
+			for (int pl = 0; pl < SPL_STATE_PLANES; pl++) {
+				uint4 v = p.state[pl * p.stride + env];
+				w[4 * pl + 0] = v.x, w[4 * pl + 1] = v.y, w[4 * pl + 2] = v.z, w[4 * pl + 3] = v.w;
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 16; k++) w[k] = 0;
+		}
+		SplState s;
+		spl_unpack(w, s);
+
+		if (DO_STEP) {
+			const bool act = valid && (p.active == nullptr || p.active[env] != 0);
+			SplStepResult r;
+			r.reward = 0.0f, r.terminated = 0, r.info = 0;
+			if (act) {
+				spl_env_step(s, p.actions[env], p.decks + env * SPL_DECK_STRIDE, &T, g_ret_table, r);
+				spl_pack(s, w);
+#pragma unroll
+				for (int pl = 0; pl < SPL_STATE_PLANES; pl++)
+					p.state[pl * p.stride + env] = make_uint4(w[4 * pl + 0], w[4 * pl + 1], w[4 * pl + 2], w[4 * pl + 3]);
+			}
+			const bool finished = r.terminated && !(r.info & SPL_INFO_ERROR);
+			const bool do_reset = act && r.terminated && p.autoreset;
+			if (do_reset) r.info |= SPL_INFO_RESET;
+			if (valid) {
+				p.reward[env] = r.reward;
+				p.terminated[env] = (uint8_t)r.terminated;
+				p.info[env] = (uint8_t)r.info;
+			}
+			// episode statistics: warp-reduce, one atomic per counter per warp
+			if (p.stats != nullptr && __any_sync(SPL_FULL, finished)) {
+				uint32_t wcode = (s.flags & SPL_FLAG_WINNER_MASK) >> SPL_FLAG_WINNER_SHIFT;
+				bool nolegal = r.info & SPL_INFO_NOLEGAL_DRAW, limit = r.info & SPL_INFO_TURN_LIMIT;
+				uint32_t v[8];
+				v[SPL_STAT_EPISODES] = finished;
+				v[SPL_STAT_NOLEGAL_DRAWS] = finished && nolegal;
+				v[SPL_STAT_LIMIT_DRAWS] = finished && !nolegal && limit;
+				v[SPL_STAT_P0_WINS] = finished && !nolegal && !limit && wcode == 1;
+				v[SPL_STAT_P1_WINS] = finished && !nolegal && !limit && wcode == 2;
+				v[SPL_STAT_TIE_DRAWS] = finished && !nolegal && !limit && wcode == 0;
+				v[SPL_STAT_SUM_MOVES] = finished ? s.move : 0u;
+				// terminal => to_play == 0 => perspective index == player index
+				v[SPL_STAT_SUM_WINNER_PRESTIGE] = (finished && wcode) ? s.prestige[wcode - 1] : 0u;
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					uint32_t tot = __reduce_add_sync(SPL_FULL, v[k]);
+					if (lane == 0 && tot) atomicAdd(p.stats + k, (unsigned long long)tot);
+				}
+			}
+			// same-step auto-reset: queue the env for the reset kernel that follows on the stream
+			uint32_t rb = __ballot_sync(SPL_FULL, do_reset);
+			if (rb) {
+				int base = 0;
+				if (lane == 0) base = atomicAdd(p.scratch, __popc(rb));
+				base = __shfl_sync(SPL_FULL, base, 0);
+				if (do_reset) p.scratch[4 + base + __popc(rb & ((1u << lane) - 1u))] = (int32_t)env;
+			}
+		}
+
+		// legal_moves of the resulting state (all-zero once terminal, envs/splendor_env.py:81)
+		uint64_t m = 0;
+		if (p.mask != nullptr || p.next_action != nullptr) m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, &T);
+		if (p.mask != nullptr) {
+			if (p.vec_ok) spl_store_mask_tile(p.mask + ti * 32 * SPL_NUM_ACTIONS, m, lane, rows);
+			else if (valid)
+				for (int a = 0; a < SPL_NUM_ACTIONS; a++) p.mask[env * SPL_NUM_ACTIONS + a] = (int8_t)((m >> a) & 1);
+		}
+		if (p.next_action != nullptr && valid) {
+			uint64_t t = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
+			p.next_action[env] = spl_sample_action(m, p.action_key, p.env_offset + (uint64_t)env, t);
+		}
+
+		if (p.obs != nullptr) {
+			SplObsStager stage(tile, lane, w[0]);
+			spl_encode_observation(w, s, &T, stage);
+			__syncwarp();
+			spl_store_obs_tile(p.obs + ti * 32 * SPL_OBS_DIM, tile, lane, rows, p.vec_ok);
+			__syncwarp();
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset kernel: initial_state (engine/state.py:181-211) for a list of environments.
+// One warp per CTA, one environment per lane; the deck order is built in shared memory.
+//   SPL_SHUFFLE_MT19937: CPython random.Random(seed): init_by_array + shuffle by _randbelow, bit-exact
+//   SPL_SHUFFLE_PHILOX : same Fisher-Yates with a Philox4x32-10 stream keyed by (seed, episode, env)
+// ------------------------------------------------------------------------------------------------
+struct ResetParams {
+	uint4* state;
+	int64_t stride;
+	uint8_t* decks;
+	uint32_t* episode;
+	const int32_t* list;  // list[0] = count, list[4..] = env indices; nullptr => all envs 0..n-1
+	int64_t n;
+	uint64_t env_offset, seed_base;
+	const uint64_t* seeds;  // explicit engine seeds [n] or nullptr
+	int32_t* obs;
+	int8_t* mask;
+	int bump_episode;  // 0: episode <- 0 (full reset), 1: episode += 1
+	int32_t* next_action;  // nullable: fused random-legal sampler for the fresh state
+	uint64_t action_key, action_t;
+	const uint64_t* action_t_base;
+};
+
+struct SplMT {  // MT19937 state of one lane, lane-interleaved in shared memory (conflict-free)
+	uint32_t* mt;
+	int idx;
+	__device__ __forceinline__ uint32_t& at(int i) { return mt[i * 32]; }
+	__device__ void seed(uint64_t a) {  // random.Random(a): init_by_array over the 32-bit words of a
+		uint32_t key[2] = {(uint32_t)a, (uint32_t)(a >> 32)};
+		int klen = key[1] ? 2 : 1;
+		at(0) = 19650218u;
+		for (int i = 1; i < 624; i++) at(i) = 1812433253u * (at(i - 1) ^ (at(i - 1) >> 30)) + (uint32_t)i;
+		int i = 1, j = 0;
+		for (int k = 624; k; k--) {
+			at(i) = (at(i) ^ ((at(i - 1) ^ (at(i - 1) >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+			i++, j++;
+			if (i >= 624) at(0) = at(623), i = 1;
+			if (j >= klen) j = 0;
+		}
+		for (int k = 623; k; k--) {
+			at(i) = (at(i) ^ ((at(i - 1) ^ (at(i - 1) >> 30)) * 1566083941u)) - (uint32_t)i;
+			i++;
+			if (i >= 624) at(0) = at(623), i = 1;
+		}
+		at(0) = 0x80000000u;
+		idx = 624;
+	}
+	__device__ uint32_t next() {
+		if (idx >= 624) {
+			for (int kk = 0; kk < 624; kk++) {
+				uint32_t y = (at(kk) & 0x80000000u) | (at((kk + 1) % 624) & 0x7fffffffu);
+				at(kk) = at((kk + 397) % 624) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+			}
+			idx = 0;
+		}
+		uint32_t y = at(idx++);
+		y ^= y >> 11;
+		y ^= (y << 7) & 0x9d2c5680u;
+		y ^= (y << 15) & 0xefc60000u;
+		y ^= y >> 18;
+		return y;
+	}
+	__device__ uint32_t randbelow(uint32_t n) {  // Lib/random.py _randbelow_with_getrandbits
+		int k = 32 - __clz(n);
+		uint32_t r = next() >> (32 - k);
+		while (r >= n) r = next() >> (32 - k);
+		return r;
+	}
+};
+
+struct SplPhiloxStream {
+	uint32_t k0, k1, c1, c2, c3, blk;
+	uint4 buf;
+	int have;
+	__device__ __forceinline__ void init(uint64_t seed, uint64_t genv, uint32_t episode) {
+		k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+		c1 = (uint32_t)genv, c2 = (uint32_t)(genv >> 32), c3 = episode;
+		blk = 0, have = 0;
+	}
+	__device__ __forceinline__ uint32_t next() {
+		if (have == 0) {
+			buf = spl_philox(make_uint4(blk++, c1, c2, c3), k0, k1);
+			have = 4;
+		}
+		uint32_t v = have == 4 ? buf.x : (have == 3 ? buf.y : (have == 2 ? buf.z : buf.w));
+		have--;
+		return v;
+	}
+	__device__ __forceinline__ uint32_t randbelow(uint32_t n) {  // Lemire's unbiased bounded integer
+		uint64_t m = (uint64_t)next() * n;
+		uint32_t l = (uint32_t)m;
+		if (l < n) {
+			uint32_t t = (0u - n) % n;
+			while (l < t) {
+				m = (uint64_t)next() * n;
+				l = (uint32_t)m;
+			}
+		}
+		return (uint32_t)(m >> 32);
+	}
+};
+
+template <class Rng>
+__device__ __forceinline__ void spl_shuffle_bytes(Rng& rng, uint8_t* x, int len) {  // Lib/random.py shuffle
+	for (int i = len - 1; i >= 1; i--) {
+		uint32_t j = rng.randbelow((uint32_t)(i + 1));
+		uint8_t t = x[i];
+		x[i] = x[j];
+		x[j] = t;
+	}
+}
+
+template <class Rng>
+__device__ __forceinline__ void spl_deal(Rng& rng, uint8_t* deck, SplState& s) {
+	spl_fresh_state(s);
+	const int off[3] = {0, 40, 70}, len[3] = {40, 30, 20};
+	for (int k = 0; k < SPL_DECK_STRIDE; k++) deck[k] = k < 90 ? (uint8_t)k : (uint8_t)SPL_EMPTY;
+	uint32_t dn = 0;
+	for (int t = 0; t < 3; t++) {  // engine/state.py:188-191
+		spl_shuffle_bytes(rng, deck + off[t], len[t]);
+		uint32_t b = 0;
+		for (int i = 0; i < 4; i++) b |= (uint32_t)deck[off[t] + len[t] - 1 - i] << (8 * i);  // pop() from the end
+		s.board[t] = b;
+		dn |= (uint32_t)(len[t] - 4) << (8 * t);
+	}
+	s.deckn = dn;
+	uint8_t nob[10];
+	for (int i = 0; i < 10; i++) nob[i] = (uint8_t)i;
+	spl_shuffle_bytes(rng, nob, 10);  // engine/state.py:193-195
+	s.nobles = (uint32_t)nob[0] | ((uint32_t)nob[1] << 8) | ((uint32_t)nob[2] << 16);
+}
+
+template <int SHUFFLE>
+__global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	SplTables* T = reinterpret_cast<SplTables*>(smem);
+	uint32_t* tile = reinterpret_cast<uint32_t*>(smem + sizeof(SplTables));
+	uint8_t* decks_s = smem + sizeof(SplTables) + SPL_TILE_WORDS * 4;
+	uint32_t* mt_s = reinterpret_cast<uint32_t*>(decks_s + 32 * SPL_DECK_SMEM);
+	const int lane = threadIdx.x;
+	{
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(T);
+		for (int i = lane; i < (int)(sizeof(SplTables) / 4); i += 32) dst[i] = src[i];
+	}
+	__syncwarp();
+	const int64_t count = p.list ? (int64_t)p.list[0] : p.n;
+	for (int64_t g = blockIdx.x; g * 32 < count; g += gridDim.x) {
+		const int64_t item = g * 32 + lane;
+		const bool valid = item < count;
+		const int64_t env = valid ? (p.list ? (int64_t)p.list[4 + item] : item) : 0;
+		uint8_t* deck = decks_s + lane * SPL_DECK_SMEM;
+		SplState s;
+		uint32_t w[16];
+		if (valid) {
+			uint32_t ep = p.bump_episode ? p.episode[env] + 1u : 0u;
+			p.episode[env] = ep;
+			uint64_t genv = p.env_offset + (uint64_t)env;
+			uint64_t seed = p.seeds ? p.seeds[env] : (p.seed_base + 1000003ull * ep + genv) % 2147483647ull;
+			if (SHUFFLE == SPL_SHUFFLE_MT19937) {
+				SplMT rng;
+				rng.mt = mt_s + lane;
+				rng.seed(seed);
+				spl_deal(rng, deck, s);
+			} else {
+				SplPhiloxStream rng;
+				rng.init(p.seeds ? seed : p.seed_base, genv, ep);
+				spl_deal(rng, deck, s);
+			}
+			spl_pack(s, w);
+#pragma unroll
+			for (int pl = 0; pl < SPL_STATE_PLANES; pl++)
+				p.state[pl * p.stride + env] = make_uint4(w[4 * pl + 0], w[4 * pl + 1], w[4 * pl + 2], w[4 * pl + 3]);
+			const uint32_t* d4 = reinterpret_cast<const uint32_t*>(deck);
+			uint32_t* g4 = reinterpret_cast<uint32_t*>(p.decks + env * SPL_DECK_STRIDE);
+#pragma unroll
+			for (int k = 0; k < SPL_DECK_STRIDE / 4; k++) g4[k] = d4[k];
+		} else {
+			spl_fresh_state(s);
+			spl_pack(s, w);
+		}
+		if (p.mask != nullptr || p.next_action != nullptr) {  // rows are scattered: one row per warp iteration, 45 coalesced bytes
+			uint64_t m = spl_legal_mask(s, T);
+			if (p.next_action != nullptr && valid) {
+				uint64_t t = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
+				p.next_action[env] = spl_sample_action(m, p.action_key, p.env_offset + (uint64_t)env, t);
+			}
+			if (p.mask != nullptr)
+			for (int r = 0; r < 32; r++) {
+				int64_t e = __shfl_sync(SPL_FULL, env, r);
+				uint64_t mr = __shfl_sync(SPL_FULL, m, r);
+				if (g * 32 + r < count) {
+					p.mask[e * SPL_NUM_ACTIONS + lane] = (int8_t)((mr >> lane) & 1);
+					if (lane < SPL_NUM_ACTIONS - 32) p.mask[e * SPL_NUM_ACTIONS + 32 + lane] = (int8_t)((mr >> (32 + lane)) & 1);
+				}
+			}
+		}
+		if (p.obs != nullptr) {
+			SplObsStager stage(tile, lane, w[0]);
+			spl_encode_observation(w, s, T, stage);
+			__syncwarp();
+			const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+			for (int r = 0; r < 32; r++) {
+				int64_t e = __shfl_sync(SPL_FULL, env, r);
+				if (g * 32 + r < count) {
+#pragma unroll
+					for (int c = lane; c < SPL_OBS_DIM; c += 32) p.obs[e * SPL_OBS_DIM + c] = (int32_t)tb[SPL_OBS_DIM * r + c];
+				}
+			}
+			__syncwarp();
+		}
+	}
+}
+
+// reset_mask[n] -> work list (count in list[0], indices from list[4])
+__global__ void spl_compact_kernel(const uint8_t* __restrict__ flags, int64_t n, int32_t* list) {
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	bool f = i < n && flags[i] != 0;
+	uint32_t b = __ballot_sync(SPL_FULL, f);
+	if (b) {
+		int lane = threadIdx.x & 31, base = 0;
+		if (lane == 0) base = atomicAdd(list, __popc(b));
+		base = __shfl_sync(SPL_FULL, base, 0);
+		if (f) list[4 + base + __popc(b & ((1u << lane) - 1u))] = (int32_t)i;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels: random legal action from an int8 mask, export / import, dual-step bookkeeping
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) spl_random_action_kernel(const int8_t* __restrict__ mask, int64_t n, uint64_t env_offset,
+                                                              uint64_t key, uint64_t t, int32_t* __restrict__ actions) {
+	__shared__ uint8_t rows[4][32 * SPL_NUM_ACTIONS];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t ntiles = (n + 31) >> 5;
+	for (int64_t ti = (int64_t)blockIdx.x * 4 + warp; ti < ntiles; ti += (int64_t)gridDim.x * 4) {
+		const int rowsv = (int)min((int64_t)32, n - ti * 32);
+		const int8_t* g = mask + ti * 32 * SPL_NUM_ACTIONS;
+		for (int b = lane; b < rowsv * SPL_NUM_ACTIONS; b += 32) rows[warp][b] = (uint8_t)g[b];
+		__syncwarp();
+		if (lane < rowsv) {
+			uint64_t m = 0;
+			for (int a = 0; a < SPL_NUM_ACTIONS; a++) m |= (uint64_t)(rows[warp][lane * SPL_NUM_ACTIONS + a] != 0) << a;
+			int64_t env = ti * 32 + lane;
+			actions[env] = spl_sample_action(m, key, env_offset + (uint64_t)env, t);
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void spl_export_kernel(const uint4* state, int64_t stride, const uint8_t* decks, int64_t n, int32_t* rows) {
+	int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (env >= n) return;
+	uint32_t w[16];
+	for (int pl = 0; pl < SPL_STATE_PLANES; pl++) {
+		uint4 v = state[pl * stride + env];
+		w[4 * pl + 0] = v.x, w[4 * pl + 1] = v.y, w[4 * pl + 2] = v.z, w[4 * pl + 3] = v.w;
+	}
+	SplState s;
+	spl_unpack(w, s);
+	spl_export_row(s, decks + env * SPL_DECK_STRIDE, rows + env * SPL_ROW_LEN);
+}
+
+__global__ void spl_import_kernel(uint4* state, int64_t stride, uint8_t* decks, int64_t n, const int32_t* rows, const uint8_t* which) {
+	int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (env >= n || (which && !which[env])) return;
+	SplState s;
+	uint32_t w[16];
+	spl_import_row(rows + env * SPL_ROW_LEN, s, decks + env * SPL_DECK_STRIDE);
+	spl_pack(s, w);
+	for (int pl = 0; pl < SPL_STATE_PLANES; pl++)
+		state[pl * stride + env] = make_uint4(w[4 * pl + 0], w[4 * pl + 1], w[4 * pl + 2], w[4 * pl + 3]);
+}
+
+// final_rewards[player] (envs/splendor_env.py:92-115) from an info byte; 0 when absent
+__device__ __forceinline__ float spl_final_reward(uint32_t info, uint32_t player) {
+	if (!(info & SPL_INFO_TERMINATED) || (info & (SPL_INFO_NOLEGAL_DRAW | SPL_INFO_ERROR))) return 0.0f;
+	uint32_t wcode = (info & SPL_INFO_WINNER_MASK) >> SPL_INFO_WINNER_SHIFT;
+	if (wcode == 0) return (info & SPL_INFO_TURN_LIMIT) ? -0.1f : 0.0f;
+	return (wcode - 1 == player) ? 1.0f : -1.0f;
+}
+
+// wrappers/dual_step_native.py:132-167: phase 1 = agent (player 0), phase 2 = opponent (player 1)
+__global__ void spl_dual_combine_kernel(const float* r1, const uint8_t* t1, const uint8_t* i1, const float* r2, const uint8_t* t2,
+                                        const uint8_t* i2, int64_t n, float* agent_reward, float* opp_reward, uint8_t* done) {
+	int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n) return;
+	if (t1[e]) {  // game ended on the agent's move (:132-145)
+		agent_reward[e] = r1[e];
+		opp_reward[e] = spl_final_reward(i1[e], 1);
+		done[e] = 1;
+	} else if (i1[e] & (SPL_INFO_ILLEGAL | SPL_INFO_ERROR)) {  // agent move rejected: opponent does not move
+		agent_reward[e] = r1[e];
+		opp_reward[e] = 0.0f;
+		done[e] = 0;
+	} else {  // (:157-167)
+		agent_reward[e] = t2[e] ? spl_final_reward(i2[e], 0) : 0.0f;
+		opp_reward[e] = r2[e];
+		done[e] = t2[e];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static int g_inited_device = -1;
+static int g_num_sms = 0;
+static int g_step_ctas_per_sm = 0, g_obs_ctas_per_sm = 0;
+static uint64_t g_host_ret[SPL_RET_TABLE_LEN];
+static bool g_host_ret_built = false;
+static int64_t g_launches = 0;
+// optional per-launch timing of the step kernel (bench.py roofline leg): CUDA events recorded on the
+// caller's stream right around the kernel
+#define SPL_TIMING_POOL 4096
+static cudaEvent_t g_ev[2 * SPL_TIMING_POOL];
+static int g_ev_created = 0, g_ev_used = 0, g_timing = 0;
+
+#define SPL_MT_SMEM (sizeof(SplTables) + SPL_TILE_WORDS * 4 + 32 * SPL_DECK_SMEM + 624 * 32 * 4)
+#define SPL_PHILOX_SMEM (sizeof(SplTables) + SPL_TILE_WORDS * 4 + 32 * SPL_DECK_SMEM)
+
+#define SPL_CUDA(x)                      \
+	do {                                 \
+		cudaError_t e_ = (x);            \
+		if (e_ != cudaSuccess) return (int)e_; \
+	} while (0)
+
+extern "C" {
+
+int spl_version(void) { return 100; }
+
+int spl_timing_enable(int on) {
+	if (on && !g_ev_created) {
+		for (int i = 0; i < 2 * SPL_TIMING_POOL; i++) SPL_CUDA(cudaEventCreate(&g_ev[i]));
+		g_ev_created = 1;
+	}
+	g_timing = on;
+	g_ev_used = 0;
+	return 0;
+}
+
+// synchronises the device; returns the summed duration and the number of timed step-kernel launches
+int spl_timing_read(double* total_ms, int64_t* count) {
+	SPL_CUDA(cudaDeviceSynchronize());
+	double tot = 0;
+	for (int i = 0; i < g_ev_used; i++) {
+		float ms = 0;
+		SPL_CUDA(cudaEventElapsedTime(&ms, g_ev[2 * i], g_ev[2 * i + 1]));
+		tot += ms;
+	}
+	*total_ms = tot;
+	*count = g_ev_used;
+	g_ev_used = 0;
+	return 0;
+}
+
+int64_t spl_launch_count(void) { return g_launches; }
+
+const char* spl_error_string(int code) {
+	if (code == 0) return "ok";
+	if (code == SPL_E_BADARG) return "splendor_b200: bad argument";
+	if (code == SPL_E_NOTINIT) return "splendor_b200: spl_init() has not been called on this device";
+	if (code == SPL_E_ALIGN) return "splendor_b200: state pointer must be 16-byte aligned";
+	if (code > 0) return cudaGetErrorString((cudaError_t)code);
+	return "splendor_b200: unknown error";
+}
+
+int spl_host_ret_table(uint64_t* out) {
+	if (!g_host_ret_built) {
+		spl_build_ret_table(g_host_ret);
+		g_host_ret_built = true;
+	}
+	memcpy(out, g_host_ret, sizeof(g_host_ret));
+	return 0;
+}
+
+int spl_init(void) {
+	int dev = 0;
+	SPL_CUDA(cudaGetDevice(&dev));
+	if (g_inited_device == dev) return 0;
+	SplTables T;
+	spl_build_tables(&T);
+	if (!g_host_ret_built) {
+		spl_build_ret_table(g_host_ret);
+		g_host_ret_built = true;
+	}
+	SPL_CUDA(cudaMemcpyToSymbol(g_tables, &T, sizeof(T)));
+	SPL_CUDA(cudaMemcpyToSymbol(g_ret_table, g_host_ret, sizeof(g_host_ret)));
+	SPL_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+	SPL_CUDA(cudaFuncSetAttribute(spl_reset_kernel<SPL_SHUFFLE_MT19937>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPL_MT_SMEM));
+	SPL_CUDA(cudaFuncSetAttribute(spl_reset_kernel<SPL_SHUFFLE_PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPL_PHILOX_SMEM));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_step_ctas_per_sm, spl_step_kernel<true>, SPL_WARPS_PER_CTA * 32, 0));
+	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_obs_ctas_per_sm, spl_step_kernel<false>, SPL_WARPS_PER_CTA * 32, 0));
+	if (g_step_ctas_per_sm < 1) g_step_ctas_per_sm = 1;
+	if (g_obs_ctas_per_sm < 1) g_obs_ctas_per_sm = 1;
+	SPL_CUDA(cudaDeviceSynchronize());
+	g_inited_device = dev;
+	return 0;
+}
+
+static int check_envs(const spl_envs_t* e) {
+	if (!e || !e->state || !e->decks || !e->episode || !e->scratch || e->n <= 0 || e->stride < e->n) return SPL_E_BADARG;
+	if (((uintptr_t)e->state & 15) || ((uintptr_t)e->decks & 15)) return SPL_E_ALIGN;
+	if (g_inited_device < 0) return SPL_E_NOTINIT;
+	return 0;
+}
+
+static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t* seeds, int bump, int32_t* obs, int8_t* mask,
+                        cudaStream_t st, const spl_step_io_t* io = nullptr) {
+	ResetParams p;
+	p.next_action = io ? io->next_action : nullptr;
+	p.action_key = io ? io->action_key : 0, p.action_t = io ? io->action_t : 0;
+	p.action_t_base = io ? io->action_t_base : nullptr;
+	p.state = (uint4*)e->state, p.stride = e->stride, p.decks = e->decks, p.episode = e->episode, p.list = list;
+	p.n = e->n, p.env_offset = e->env_offset, p.seed_base = e->seed_base, p.seeds = seeds, p.obs = obs, p.mask = mask;
+	p.bump_episode = bump;
+	int64_t groups = (e->n + 31) / 32;
+	if (e->shuffle_mode == SPL_SHUFFLE_MT19937) {
+		int grid = (int)(groups < (int64_t)g_num_sms * 2 ? groups : (int64_t)g_num_sms * 2);
+		spl_reset_kernel<SPL_SHUFFLE_MT19937><<<grid, 32, SPL_MT_SMEM, st>>>(p);
+	} else if (e->shuffle_mode == SPL_SHUFFLE_PHILOX) {
+		int grid = (int)(groups < (int64_t)g_num_sms * 12 ? groups : (int64_t)g_num_sms * 12);
+		spl_reset_kernel<SPL_SHUFFLE_PHILOX><<<grid, 32, SPL_PHILOX_SMEM, st>>>(p);
+	} else {
+		return SPL_E_BADARG;
+	}
+	g_launches++;
+	return (int)cudaGetLastError();
+}
+
+int spl_reset(const spl_envs_t* envs, const uint64_t* seeds, const uint8_t* reset_mask, int32_t* obs, int8_t* mask, void* stream) {
+	int rc = check_envs(envs);
+	if (rc) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (reset_mask == nullptr) return launch_reset(envs, nullptr, seeds, 0, obs, mask, st);
+	SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, 16, st));
+	spl_compact_kernel<<<(unsigned)((envs->n + 255) / 256), 256, 0, st>>>(reset_mask, envs->n, envs->scratch);
+	g_launches++;
+	SPL_CUDA(cudaGetLastError());
+	return launch_reset(envs, envs->scratch, seeds, 1, obs, mask, st);
+}
+
+static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, int32_t* obs, int8_t* mask, cudaStream_t st) {
+	StepParams p;
+	p.state = (uint4*)e->state, p.stride = e->stride, p.decks = e->decks, p.scratch = e->scratch, p.n = e->n;
+	p.env_offset = e->env_offset;
+	p.actions = io ? io->actions : nullptr, p.active = io ? io->active : nullptr;
+	p.obs = obs, p.mask = mask;
+	p.reward = io ? io->reward : nullptr, p.terminated = io ? io->terminated : nullptr, p.info = io ? io->info : nullptr;
+	p.stats = io ? (unsigned long long*)io->stats : nullptr;
+	p.next_action = io ? io->next_action : nullptr;
+	p.action_key = io ? io->action_key : 0, p.action_t = io ? io->action_t : 0;
+	p.action_t_base = io ? io->action_t_base : nullptr;
+	p.autoreset = io ? io->autoreset : 0;
+	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;
+	int64_t ctas = ((e->n + 31) / 32 + SPL_WARPS_PER_CTA - 1) / SPL_WARPS_PER_CTA;
+	int64_t cap = (int64_t)g_num_sms * (do_step ? g_step_ctas_per_sm : g_obs_ctas_per_sm);
+	int grid = (int)(ctas < cap ? ctas : cap);
+	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
+	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
+	if (do_step) spl_step_kernel<true><<<grid, SPL_WARPS_PER_CTA * 32, 0, st>>>(p);
+	else spl_step_kernel<false><<<grid, SPL_WARPS_PER_CTA * 32, 0, st>>>(p);
+	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
+	g_launches++;
+	return (int)cudaGetLastError();
+}
+
+int spl_step(const spl_envs_t* envs, const spl_step_io_t* io, void* stream) {
+	int rc = check_envs(envs);
+	if (rc) return rc;
+	if (!io || !io->actions || !io->reward || !io->terminated || !io->info) return SPL_E_BADARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (io->autoreset) SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, 16, st));
+	rc = launch_step(envs, io, true, io->obs, io->mask, st);
+	if (rc) return rc;
+	if (io->autoreset) {
+		// the reset kernel also re-samples next_action for the envs whose mask it replaces
+		rc = launch_reset(envs, envs->scratch, nullptr, 1, io->obs, io->mask, st, io);
+		if (rc) return rc;
+	}
+	return 0;
+}
+
+int spl_observe(const spl_envs_t* envs, int32_t* obs, int8_t* mask, void* stream) {
+	int rc = check_envs(envs);
+	if (rc) return rc;
+	return launch_step(envs, nullptr, false, obs, mask, (cudaStream_t)stream);
+}
+
+int spl_random_action(const int8_t* mask, int64_t n, uint64_t env_offset, uint64_t key, uint64_t t, int32_t* actions, void* stream) {
+	if (!mask || !actions || n <= 0) return SPL_E_BADARG;
+	if (g_inited_device < 0) return SPL_E_NOTINIT;
+	int64_t ctas = ((n + 31) / 32 + 3) / 4;
+	int64_t cap = (int64_t)g_num_sms * 8;
+	spl_random_action_kernel<<<(int)(ctas < cap ? ctas : cap), 128, 0, (cudaStream_t)stream>>>(mask, n, env_offset, key, t, actions);
+	g_launches++;
+	return (int)cudaGetLastError();
+}
+
+int spl_export_state(const spl_envs_t* envs, int32_t* rows, void* stream) {
+	int rc = check_envs(envs);
+	if (rc) return rc;
+	if (!rows) return SPL_E_BADARG;
+	spl_export_kernel<<<(unsigned)((envs->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4*)envs->state, envs->stride,
+	                                                                                    envs->decks, envs->n, rows);
+	g_launches++;
+	return (int)cudaGetLastError();
+}
+
+int spl_import_state(const spl_envs_t* envs, const int32_t* rows, const uint8_t* which, void* stream) {
+	int rc = check_envs(envs);
+	if (rc) return rc;
+	if (!rows) return SPL_E_BADARG;
+	spl_import_kernel<<<(unsigned)((envs->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)envs->state, envs->stride, envs->decks,
+	                                                                                    envs->n, rows, which);
+	g_launches++;
+	return (int)cudaGetLastError();
+}
+
+int spl_dual_combine(const float* r1, const uint8_t* term1, const uint8_t* info1, const float* r2, const uint8_t* term2,
+                     const uint8_t* info2, int64_t n, float* agent_reward, float* opp_reward, uint8_t* done, void* stream) {
+	if (!r1 || !term1 || !info1 || !r2 || !term2 || !info2 || !agent_reward || !opp_reward || !done || n <= 0) return SPL_E_BADARG;
+	spl_dual_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r1, term1, info1, r2, term2, info2, n,
+	                                                                                    agent_reward, opp_reward, done);
+	g_launches++;
+	return (int)cudaGetLastError();
+}
+
+}  // extern "C"

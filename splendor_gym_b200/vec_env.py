@@ -1,0 +1,233 @@
+"""SplendorVecEnv -- N lock-stepped Splendor games resident in HBM.
+
+Host-side mirror of the reference's vector contract (what ppo_splendor.py:164-173,219-297 consumes from
+``gym.vector.SyncVectorEnv`` / the per-env ``dual_step`` loop): observations ``[N,297] int32``, action masks
+``[N,45] int8``, rewards ``[N] float32``, terminations ``[N] bool``, same-step auto-reset.  PyTorch only owns
+the device buffers and the stream; every computation is a kernel of libsplendor_b200.so reached through
+the C ABI (include/splendor_b200.h).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class SplendorVecEnv:
+    """Batched ``SplendorEnv`` (splendor_gym/envs/splendor_env.py:23-130).
+
+    Parameters
+    ----------
+    num_envs : environments in this shard.
+    device : CUDA device.
+    seed : base of the per-episode engine-seed schedule; engine seed of (global env g, episode e) is
+        ``(seed + 1000003*e + g) mod (2**31-1)`` (the reference draws it from a per-env PCG64 stream,
+        envs/splendor_env.py:42-43; explicit engine seeds can be passed to ``reset(seeds=...)``).
+    shuffle : ``"mt19937"`` = decks bit-identical to ``initial_state(seed)`` (engine/state.py:181-195);
+        ``"philox"`` = native counter-based shuffle (distribution-equivalent, faster).
+    env_offset : global index of env 0 (multi-GPU sharding; results do not depend on the GPU count).
+    autoreset : same-step auto-reset as in ppo_splendor.py:245-250 (reward/terminated of the finished
+        episode, observation/mask of the new one).
+    """
+
+    num_actions = L.NUM_ACTIONS
+    obs_dim = L.OBS_DIM
+
+    def __init__(self, num_envs: int, device="cuda", seed: int = 0, shuffle: str = "philox", env_offset: int = 0,
+                 autoreset: bool = True):
+        if num_envs <= 0:
+            raise ValueError("num_envs must be positive")
+        self.lib = L.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.SplendorB200Error("SplendorVecEnv needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n = int(num_envs)
+        self.autoreset = bool(autoreset)
+        self.shuffle_mode = {"mt19937": L.SHUFFLE_MT19937, "philox": L.SHUFFLE_PHILOX}[shuffle]
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_init(), "spl_init")
+        d, n = self.device, self.n
+        # structure-of-arrays state in HBM: 4 planes x N x 16 B (hot), N x 96 B deck order (cold)
+        self.state = torch.zeros((L.STATE_PLANES, n, 16), dtype=torch.uint8, device=d)
+        self.decks = torch.zeros((n, L.DECK_STRIDE), dtype=torch.uint8, device=d)
+        self.episode = torch.zeros(n, dtype=torch.int32, device=d)
+        self.scratch = torch.zeros(n + 4, dtype=torch.int32, device=d)
+        self.obs = torch.zeros((n, L.OBS_DIM), dtype=torch.int32, device=d)
+        self.mask = torch.zeros((n, L.NUM_ACTIONS), dtype=torch.int8, device=d)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=d)
+        self._terminated = torch.zeros(n, dtype=torch.uint8, device=d)
+        self.terminated = self._terminated.view(torch.bool)
+        self.truncated = torch.zeros(n, dtype=torch.bool, device=d)
+        self.info_bits = torch.zeros(n, dtype=torch.uint8, device=d)
+        self.stats = torch.zeros(8, dtype=torch.int64, device=d)
+        self.next_action = torch.zeros(n, dtype=torch.int32, device=d)
+        self._envs = L.SplEnvs(
+            state=self.state.data_ptr(), decks=self.decks.data_ptr(), episode=self.episode.data_ptr(),
+            scratch=self.scratch.data_ptr(), stride=n, n=n, env_offset=int(env_offset), seed_base=int(seed),
+            shuffle_mode=self.shuffle_mode, reserved_=0,
+        )
+        self._io = L.SplStepIO()
+        self._t = 0  # lock-step counter (drives the Philox action stream)
+        self.t_base = None  # optional device int64 scalar added to the counter (CUDA-graph replays)
+        self.action_key = 0xB200
+        self._is_reset = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def info(self) -> Dict[str, torch.Tensor]:
+        """The reference's info dict, batched (envs/splendor_env.py:47-48,82-88)."""
+        b = self.info_bits
+        return {
+            "action_mask": self.mask,
+            "to_play": self.obs[:, 294],
+            "illegal_action": (b & L.INFO_ILLEGAL) != 0,
+            "draw": (b & L.INFO_NOLEGAL_DRAW) != 0,
+            "turn_limit": (b & L.INFO_TURN_LIMIT) != 0,
+            "winner": ((b & L.INFO_WINNER_MASK) >> L.INFO_WINNER_SHIFT).to(torch.int8) - 1,
+            "error": (b & L.INFO_ERROR) != 0,
+            "reset": (b & L.INFO_RESET) != 0,
+            "info_bits": b,
+        }
+
+    @staticmethod
+    def final_rewards(info_bits: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``SplendorEnv.get_final_rewards`` (envs/splendor_env.py:92-115) from info bits -> (r0, r1, present)."""
+        b = info_bits.to(torch.int32)
+        present = ((b & L.INFO_TERMINATED) != 0) & ((b & (L.INFO_NOLEGAL_DRAW | L.INFO_ERROR)) == 0)
+        w = ((b & L.INFO_WINNER_MASK) >> L.INFO_WINNER_SHIFT) - 1
+        draw = torch.where((b & L.INFO_TURN_LIMIT) != 0, -0.1, 0.0).to(torch.float32)
+        r0 = torch.where(w < 0, draw, torch.where(w == 0, 1.0, -1.0).to(torch.float32))
+        r1 = torch.where(w < 0, draw, torch.where(w == 1, 1.0, -1.0).to(torch.float32))
+        zero = torch.zeros_like(r0)
+        return torch.where(present, r0, zero), torch.where(present, r1, zero), present
+
+    # ------------------------------------------------------------------ reset / step
+    def reset(self, *, seed: Optional[int] = None, seeds: Optional[torch.Tensor] = None,
+              reset_mask: Optional[torch.Tensor] = None, options=None):
+        """``SplendorEnv.reset`` for all envs (or those flagged in ``reset_mask``) -> (obs, info)."""
+        if seed is not None:
+            self._envs.seed_base = int(seed)
+        if seeds is not None:
+            seeds = seeds.to(device=self.device, dtype=torch.int64).contiguous()
+        if reset_mask is not None:
+            reset_mask = reset_mask.to(device=self.device).view(-1).to(torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_reset(C.byref(self._envs), _ptr(seeds), _ptr(reset_mask), self.obs.data_ptr(),
+                                       self.mask.data_ptr(), self._stream()), "spl_reset")
+        if reset_mask is None:
+            self._t = 0
+        self._is_reset = True
+        return self.obs, {"action_mask": self.mask, "to_play": self.obs[:, 294]}
+
+    def step(self, actions: torch.Tensor, *, active: Optional[torch.Tensor] = None, out_obs: Optional[torch.Tensor] = None,
+             out_mask: Optional[torch.Tensor] = None, sample_next: bool = False, autoreset: Optional[bool] = None,
+             out_reward: Optional[torch.Tensor] = None, out_terminated: Optional[torch.Tensor] = None,
+             out_next_action: Optional[torch.Tensor] = None, write_obs: bool = True):
+        """``SplendorEnv.step`` for every env in lock-step -> (obs, reward, terminated, truncated, info).
+
+        ``out_obs`` / ``out_mask`` redirect the observation / mask of this step into caller storage (e.g. a
+        rollout buffer slice).  ``sample_next`` also draws a uniform random legal action for the returned
+        mask into ``self.next_action`` (fused; same stream as ``sample_random_actions``).
+        """
+        assert self._is_reset, "Call reset() first"
+        if actions.dtype != torch.int32 or not actions.is_contiguous() or actions.device != self.device:
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        if active is not None:
+            active = active.to(device=self.device).view(-1).to(torch.uint8).contiguous()
+        obs = self.obs if out_obs is None else out_obs
+        mask = self.mask if out_mask is None else out_mask
+        io = self._io
+        io.actions, io.active = actions.data_ptr(), _ptr(active)
+        reward = self.reward if out_reward is None else out_reward
+        term = self._terminated if out_terminated is None else out_terminated
+        nxt = self.next_action if out_next_action is None else out_next_action
+        io.obs, io.mask = (obs.data_ptr() if write_obs else None), mask.data_ptr()
+        io.reward, io.terminated, io.info = reward.data_ptr(), term.data_ptr(), self.info_bits.data_ptr()
+        io.stats = self.stats.data_ptr()
+        io.next_action = nxt.data_ptr() if (sample_next or out_next_action is not None) else None
+        io.action_key, io.action_t = self.action_key, self._t + 1
+        io.action_t_base = _ptr(self.t_base)
+        io.autoreset = int(self.autoreset if autoreset is None else autoreset)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_step(C.byref(self._envs), C.byref(io), self._stream()), "spl_step")
+        self._t += 1
+        if out_reward is not None or out_terminated is not None:
+            return obs, reward, term.view(torch.bool), self.truncated, None
+        return obs, self.reward, self.terminated, self.truncated, self.info()
+
+    def observe(self, out_obs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None):
+        """encode_observation + legal_moves of the current states (no step)."""
+        obs = self.obs if out_obs is None else out_obs
+        mask = self.mask if out_mask is None else out_mask
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_observe(C.byref(self._envs), obs.data_ptr(), mask.data_ptr(), self._stream()), "spl_observe")
+        return obs, mask
+
+    def sample_random_actions(self, mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``random_opponent`` (wrappers/selfplay.py:66-73) for every env: uniform over the legal actions."""
+        mask = self.mask if mask is None else mask
+        out = self.next_action if out is None else out
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_random_action(mask.data_ptr(), self.n, self._envs.env_offset, self.action_key, self._t,
+                                               out.data_ptr(), self._stream()), "spl_random_action")
+        return out
+
+    # ------------------------------------------------------------------ state exchange (tests, debugging)
+    def export_state(self) -> torch.Tensor:
+        rows = torch.empty((self.n, L.ROW_LEN), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_export_state(C.byref(self._envs), rows.data_ptr(), self._stream()), "spl_export_state")
+        return rows
+
+    def import_state(self, rows: torch.Tensor, which: Optional[torch.Tensor] = None) -> None:
+        rows = rows.to(device=self.device, dtype=torch.int32).contiguous()
+        assert rows.shape == (self.n, L.ROW_LEN)
+        if which is not None:
+            which = which.to(device=self.device).view(-1).to(torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_import_state(C.byref(self._envs), rows.data_ptr(), _ptr(which), self._stream()), "spl_import_state")
+        self._is_reset = True
+
+    # ------------------------------------------------------------------ dual step (self-play turn)
+    def dual_step(self, agent_actions: torch.Tensor, opponent_policy: Callable[[torch.Tensor, torch.Tensor], torch.Tensor]):
+        """``DualStepNativeWrapper.dual_step`` (wrappers/dual_step_native.py:90-193), batched.
+
+        Phase 1: every env applies the agent's (player 0) action.  Phase 2: envs still running apply
+        ``opponent_policy(obs, mask) -> actions``.  Returns
+        ``(agent_obs, agent_reward, opp_obs, opp_reward, done, info)``; ``agent_obs is opp_obs`` like the
+        reference (:182-191).  An env whose agent action was rejected (illegal) skips phase 2 (the
+        reference raises there, :149-150).
+        """
+        if not hasattr(self, "_dual"):
+            d, n = self.device, self.n
+            self._dual = dict(
+                r1=torch.zeros(n, dtype=torch.float32, device=d), t1=torch.zeros(n, dtype=torch.uint8, device=d),
+                i1=torch.zeros(n, dtype=torch.uint8, device=d), agent_r=torch.zeros(n, dtype=torch.float32, device=d),
+                opp_r=torch.zeros(n, dtype=torch.float32, device=d), done=torch.zeros(n, dtype=torch.uint8, device=d),
+            )
+        D = self._dual
+        obs, _, _, _, _ = self.step(agent_actions)
+        D["r1"].copy_(self.reward)
+        D["t1"].copy_(self._terminated)
+        D["i1"].copy_(self.info_bits)
+        active = (D["t1"] == 0) & ((D["i1"] & (L.INFO_ILLEGAL | L.INFO_ERROR)) == 0)
+        opp_actions = opponent_policy(self.obs, self.mask)
+        obs, _, _, _, _ = self.step(opp_actions, active=active)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_dual_combine(D["r1"].data_ptr(), D["t1"].data_ptr(), D["i1"].data_ptr(), self.reward.data_ptr(),
+                                              self._terminated.data_ptr(), self.info_bits.data_ptr(), self.n,
+                                              D["agent_r"].data_ptr(), D["opp_r"].data_ptr(), D["done"].data_ptr(),
+                                              self._stream()), "spl_dual_combine")
+        info = {"action_mask": self.mask, "to_play": self.obs[:, 294], "info_bits_agent": D["i1"], "info_bits_opponent": self.info_bits}
+        return obs, D["agent_r"], obs, D["opp_r"], D["done"].view(torch.bool), info

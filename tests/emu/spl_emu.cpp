@@ -1,0 +1,76 @@
+// Host build of the lane-local rules (splendor_gym_b200/csrc/spl_core.cuh) for logic checks on a
+// machine without a GPU.  TEST-ONLY: the product package never loads this; it exists so that the
+// per-lane code can be compared with the oracle before (and independently of) a GPU run.
+#include <stdint.h>
+#include <string.h>
+
+#include "../../splendor_gym_b200/csrc/spl_tables_host.h"
+
+static SplTables g_T;
+static uint64_t g_ret[SPL_RET_TABLE_LEN];
+static bool g_init = false;
+static void init() {
+	if (g_init) return;
+	spl_build_tables(&g_T);
+	spl_build_ret_table(g_ret);
+	g_init = true;
+}
+
+extern "C" {
+
+void emu_ret_table(uint64_t* out) {
+	init();
+	memcpy(out, g_ret, sizeof(g_ret));
+}
+
+uint64_t emu_mt_block(uint64_t seed, uint32_t blk) { return spl_mt_top3_block(seed, blk); }
+
+// pack -> unpack round trip of a flat row
+void emu_roundtrip(const int32_t* row, int32_t* row_out) {
+	init();
+	SplState s, s2;
+	uint8_t deck[SPL_DECK_STRIDE];
+	uint32_t w[16];
+	spl_import_row(row, s, deck);
+	spl_pack(s, w);
+	spl_unpack(w, s2);
+	spl_export_row(s2, deck, row_out);
+}
+
+void emu_observe(const int32_t* row, int32_t* obs, int8_t* mask) {
+	init();
+	SplState s;
+	uint8_t deck[SPL_DECK_STRIDE];
+	uint32_t w[16];
+	spl_import_row(row, s, deck);
+	spl_pack(s, w);
+	uint64_t m = spl_is_terminal(s) ? 0 : spl_legal_mask(s, &g_T);
+	for (int i = 0; i < SPL_NUM_ACTIONS; i++) mask[i] = (int8_t)((m >> i) & 1);
+	uint32_t R[75];
+	spl_encode_observation(w, s, &g_T, [&](int k, uint32_t v) { R[k] = v; });
+	for (int i = 0; i < SPL_OBS_DIM; i++) obs[i] = (int32_t)((R[i >> 2] >> (8 * (i & 3))) & 0xFF);
+}
+
+void emu_env_step(const int32_t* row, int32_t action, int32_t* row_out, int32_t* obs, int8_t* mask, float* reward,
+                  uint8_t* terminated, uint8_t* info) {
+	init();
+	SplState s;
+	uint8_t deck[SPL_DECK_STRIDE];
+	uint32_t w[16];
+	spl_import_row(row, s, deck);
+	spl_pack(s, w);  // go through the packed form like the kernel does
+	spl_unpack(w, s);
+	SplStepResult r;
+	spl_env_step(s, action, deck, &g_T, g_ret, r);
+	spl_pack(s, w);
+	uint64_t m = spl_is_terminal(s) ? 0 : spl_legal_mask(s, &g_T);
+	for (int i = 0; i < SPL_NUM_ACTIONS; i++) mask[i] = (int8_t)((m >> i) & 1);
+	uint32_t R[75];
+	spl_encode_observation(w, s, &g_T, [&](int k, uint32_t v) { R[k] = v; });
+	for (int i = 0; i < SPL_OBS_DIM; i++) obs[i] = (int32_t)((R[i >> 2] >> (8 * (i & 3))) & 0xFF);
+	*reward = r.reward;
+	*terminated = (uint8_t)r.terminated;
+	*info = (uint8_t)r.info;
+	spl_export_row(s, deck, row_out);
+}
+}

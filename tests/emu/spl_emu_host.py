@@ -1,0 +1,70 @@
+"""ctypes loader for the test-only host build of the lane-local rules (tests/emu/spl_emu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libspl_emu.so")
+ROOT = os.path.dirname(os.path.dirname(HERE))
+_lib = None
+
+
+def build():
+    srcs = [os.path.join(HERE, "spl_emu.cpp"), os.path.join(ROOT, "splendor_gym_b200", "csrc", "spl_core.cuh"),
+            os.path.join(ROOT, "splendor_gym_b200", "csrc", "spl_tables_host.h")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(s) for s in srcs):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB, srcs[0]])
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.emu_mt_block.restype = C.c_uint64
+        _lib.emu_mt_block.argtypes = [C.c_uint64, C.c_uint32]
+    return _lib
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def env_step(row, action):
+    r = np.ascontiguousarray(row, np.int32)
+    out = np.zeros(166, np.int32)
+    obs = np.zeros(297, np.int32)
+    mask = np.zeros(45, np.int8)
+    rew, term, info = C.c_float(), C.c_uint8(), C.c_uint8()
+    lib().emu_env_step(_p(r, C.c_int32), int(action), _p(out, C.c_int32), _p(obs, C.c_int32), _p(mask, C.c_int8),
+                       C.byref(rew), C.byref(term), C.byref(info))
+    return out, obs, mask, float(rew.value), bool(term.value), int(info.value)
+
+
+def observe(row):
+    r = np.ascontiguousarray(row, np.int32)
+    obs = np.zeros(297, np.int32)
+    mask = np.zeros(45, np.int8)
+    lib().emu_observe(_p(r, C.c_int32), _p(obs, C.c_int32), _p(mask, C.c_int8))
+    return obs, mask
+
+
+def roundtrip(row):
+    r = np.ascontiguousarray(row, np.int32)
+    out = np.zeros(166, np.int32)
+    lib().emu_roundtrip(_p(r, C.c_int32), _p(out, C.c_int32))
+    return out
+
+
+def ret_table():
+    t = np.zeros(8910, np.uint64)
+    lib().emu_ret_table(_p(t, C.c_uint64))
+    return t
+
+
+def mt_block(seed, blk):
+    return int(lib().emu_mt_block(seed, blk))

@@ -1,0 +1,88 @@
+"""Host-compiled copy of the lane-local CUDA rules (splendor_gym_b200/csrc/spl_core.cuh, built by
+tests/emu) against the oracle and the golden vectors.  This checks the per-lane logic of the kernels
+on a machine without a GPU; the GPU parity tests proper are tests/test_gpu_*.py."""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+import spl_emu_host as emu
+
+
+def test_ret_table_matches_cpython_golden():
+    g = load_golden("token_return.json")
+    t = emu.ret_table()
+    assert hashlib.sha256(t.astype("<u8").tobytes()).hexdigest() == g["sha256"]
+
+
+def test_mt_block_restatement(oracle):
+    rng = np.random.RandomState(3)
+    seeds = [0, 1, 2**32 - 1, 2**32, 2**37 + 99] + [int(x) for x in rng.randint(0, 2**62, size=20)]
+    for seed in seeds:
+        outs = oracle.mt_outputs(seed, 210)
+        for blk in (0, 1, 5, 9):
+            want = 0
+            for j in range(21):
+                want |= (int(outs[21 * blk + j]) >> 29) << (3 * j)
+            assert emu.mt_block(seed, blk) == want, (seed, blk)
+
+
+def test_edge_cases_golden():
+    for c in load_golden("edge_cases.json"):
+        row_in = np.array(c["row_in"], np.int32)
+        assert emu.roundtrip(row_in).tolist() == c["row_in"], c["name"]
+        obs0, mask0 = emu.observe(row_in)
+        game_over_terminal = c.get("raises") == "RuntimeError"
+        if not game_over_terminal:
+            assert mask0.tolist() == c["mask_in"], c["name"]
+        row, obs, mask, r, term, info = emu.env_step(row_in, c["action"])
+        if "raises" in c:
+            assert info & 64 and row.tolist() == c["row_in"], c["name"]
+            continue
+        assert row.tolist() == c["row_out"], c["name"]
+        assert obs.tolist() == c["obs"], c["name"]
+        assert mask.tolist() == c["mask"], c["name"]
+        assert r == pytest.approx(c["reward"]) and term == c["terminated"] and info == c["info"], c["name"]
+
+
+@pytest.mark.parametrize("idx", range(0, 36, 3))
+def test_golden_games(idx):
+    from test_oracle_golden import digest
+
+    g = load_golden("games.json")[idx]
+    import oracle.oracle as O
+
+    row = O.initial_row(g["seed"])
+    for t, a in enumerate(g["actions"]):
+        row, obs, mask, r, term, info = emu.env_step(row, a)
+        assert digest(obs, mask, row, r, term, info) == g["digests"][t], (g["seed"], g["policy"], t)
+
+
+def test_random_games_vs_oracle(oracle):
+    rng = np.random.RandomState(11)
+    steps = 0
+    for g in range(150):
+        row = oracle.initial_row(int(rng.randint(0, 2**31 - 1)))
+        for t in range(400):
+            obs0, mask0 = emu.observe(row)
+            assert np.array_equal(mask0, oracle.legal_moves(row))
+            assert np.array_equal(obs0, oracle.encode_observation(row))
+            legal = np.flatnonzero(mask0)
+            if len(legal) == 0:
+                a = 0
+            elif rng.rand() < 0.04:
+                a = int(rng.randint(-2, 48))
+            else:
+                a = int(legal[rng.randint(len(legal))])
+            want = oracle.env_step(row, a)
+            got = emu.env_step(row, a)
+            for x, y in zip(want[:3], got[:3]):
+                assert np.array_equal(x, y), (g, t, a)
+            assert want[3] == pytest.approx(got[3]) and want[4] == got[4] and want[5] == got[5], (g, t, a)
+            row = want[0]
+            steps += 1
+            if want[4]:
+                break
+    assert steps > 8000

@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via SplendorVecEnv) against the oracle and the
+golden vectors generated from the reference.  Bit-exact: observations, masks, rewards, terminations,
+info bits and the full exported state after every step."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def VecEnv():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from splendor_gym_b200 import SplendorVecEnv
+
+    return SplendorVecEnv
+
+
+def assert_step_equal(env, out, ref_out, t, check_state=None):
+    obs, rew, term, trunc, info = out
+    robs, rrew, rterm, rinfo, rmask = ref_out
+    o, m = _np(obs), _np(info["action_mask"])
+    bad = np.flatnonzero((o != robs).any(axis=1))
+    assert bad.size == 0, f"step {t}: obs mismatch in envs {bad[:8]} cols {np.flatnonzero(o[bad[0]] != robs[bad[0]])[:12]}"
+    bad = np.flatnonzero((m != rmask).any(axis=1))
+    assert bad.size == 0, f"step {t}: mask mismatch in envs {bad[:8]}"
+    assert np.array_equal(_np(rew), rrew), f"step {t}: reward"
+    assert np.array_equal(_np(term).astype(np.uint8), rterm), f"step {t}: terminated"
+    assert np.array_equal(_np(info["info_bits"]), rinfo), f"step {t}: info bits"
+    assert not _np(trunc).any()
+    if check_state is not None:
+        rows = _np(env.export_state())
+        bad = np.flatnonzero((rows != check_state).any(axis=1))
+        assert bad.size == 0, f"step {t}: state mismatch env {bad[:4]} fields {np.flatnonzero(rows[bad[0]] != check_state[bad[0]])[:12]}"
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000])
+def test_reset_mt19937_bit_exact(VecEnv, oracle, n):
+    """spl_reset in MT mode == initial_state(seed) (engine/state.py:181-211), ragged tile sizes included."""
+    env = VecEnv(n, seed=7, shuffle="mt19937", env_offset=5)
+    obs, info = env.reset()
+    ref = oracle.OracleVec(n, seed_base=7, env_offset=5)
+    robs, rmask = ref.reset()
+    assert np.array_equal(_np(env.export_state()), ref.export_rows())
+    assert np.array_equal(_np(obs), robs) and np.array_equal(_np(info["action_mask"]), rmask)
+
+
+def test_reset_explicit_engine_seeds(VecEnv, oracle):
+    seeds = [0, 42, 123456789, 2**31 - 2, 1826701614, 191664963, 33158374, 2**32 + 5, 2**40 + 7]
+    env = VecEnv(len(seeds), shuffle="mt19937")
+    env.reset(seeds=torch.tensor(seeds, dtype=torch.int64))
+    rows = _np(env.export_state())
+    for i, s in enumerate(seeds):
+        assert np.array_equal(rows[i], oracle.initial_row(s)), s
+    g = {r["seed"]: r for r in load_golden("initial_states.json")}
+    for i, s in enumerate(seeds):
+        if s in g:
+            assert rows[i].tolist() == g[s]["row"]
+            assert _np(env.obs)[i].tolist() == oracle.encode_observation(np.array(g[s]["row"], np.int32)).tolist()
+
+
+@pytest.mark.parametrize("n,steps,illegal_rate", [(33, 260, 0.0), (4096, 300, 0.0), (2048, 200, 0.05)])
+def test_lockstep_rollout_bit_exact(VecEnv, oracle, n, steps, illegal_rate):
+    """Random-policy lock-step rollout with same-step auto-reset; every output of every step and the
+    full state are compared with the oracle (which replays the reference's rules on the same actions)."""
+    env = VecEnv(n, seed=2024, shuffle="mt19937", autoreset=True)
+    ref = oracle.OracleVec(n, seed_base=2024)
+    obs, info = env.reset()
+    robs, rmask = ref.reset()
+    assert np.array_equal(_np(obs), robs)
+    rng = np.random.RandomState(n)
+    actions = env.sample_random_actions().clone()
+    assert np.array_equal(_np(actions), ref.random_actions(env.action_key, 0))
+    for t in range(steps):
+        a = _np(actions).copy()
+        if illegal_rate > 0:
+            flip = rng.rand(n) < illegal_rate
+            a[flip] = rng.randint(-3, 50, size=int(flip.sum()))
+        out = env.step(torch.from_numpy(a).cuda(), sample_next=True)
+        ref_out = ref.step(a, autoreset=True)
+        assert_step_equal(env, out, ref_out, t, check_state=ref.export_rows() if t % 25 == 0 or t == steps - 1 else None)
+        actions = env.next_action.clone()
+        # fused sampler == standalone sampler == oracle's stream
+        assert np.array_equal(_np(actions), ref.random_actions(env.action_key, t + 1)), f"step {t}: sampled actions"
+    assert np.array_equal(_np(env.stats), ref.stats())
+    assert np.array_equal(_np(env.episode).astype(np.uint32), ref.episodes())
+    assert ref.stats()[0] > 0
+
+
+def test_edge_cases_from_reference_tests(VecEnv, oracle):
+    """Hand-built states mirroring the reference's own tests (tests/golden/edge_cases.json), injected with
+    import_state exactly as those tests mutate env.state."""
+    cases = load_golden("edge_cases.json")
+    n = len(cases)
+    env = VecEnv(n, shuffle="mt19937", autoreset=False)
+    env.import_state(torch.tensor([c["row_in"] for c in cases], dtype=torch.int32))
+    assert np.array_equal(_np(env.export_state()), np.array([c["row_in"] for c in cases], np.int32))
+    obs0, mask0 = env.observe()
+    for i, c in enumerate(cases):
+        if c.get("raises") != "RuntimeError":
+            assert _np(mask0)[i].tolist() == c["mask_in"], c["name"]
+    obs, rew, term, trunc, info = env.step(torch.tensor([c["action"] for c in cases], dtype=torch.int32))
+    rows = _np(env.export_state())
+    o, m, r, te, ib = _np(obs), _np(info["action_mask"]), _np(rew), _np(term), _np(info["info_bits"])
+    for i, c in enumerate(cases):
+        if "raises" in c:
+            assert ib[i] & 64 and rows[i].tolist() == c["row_in"], c["name"]
+            assert bool(ib[i] & 8) == (c["raises"] == "RuntimeError")
+            continue
+        assert rows[i].tolist() == c["row_out"], c["name"]
+        assert o[i].tolist() == c["obs"], c["name"]
+        assert m[i].tolist() == c["mask"], c["name"]
+        assert r[i] == pytest.approx(c["reward"]) and bool(te[i]) == c["terminated"] and int(ib[i]) == c["info"], c["name"]
+    r0, r1, present = env.final_rewards(info["info_bits"])
+    for i, c in enumerate(cases):
+        if c.get("final_rewards") is not None:
+            assert bool(present[i]) and [float(r0[i]), float(r1[i])] == pytest.approx(c["final_rewards"]), c["name"]
+        elif "raises" not in c:
+            assert not bool(present[i]), c["name"]
+
+
+def test_golden_games_replay(VecEnv):
+    """Full reference games (tests/golden/games.json) replayed on the GPU, one env per game, lock-step."""
+    from test_oracle_golden import digest
+
+    games = load_golden("games.json")
+    n = len(games)
+    env = VecEnv(n, shuffle="mt19937", autoreset=False)
+    env.reset(seeds=torch.tensor([g["seed"] for g in games], dtype=torch.int64))
+    T = max(len(g["actions"]) for g in games)
+    done = np.zeros(n, bool)
+    for t in range(T):
+        a = np.array([g["actions"][t] if t < len(g["actions"]) else 0 for g in games], np.int32)
+        active = np.array([t < len(g["actions"]) for g in games])
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(a).cuda(), active=torch.from_numpy(active).cuda())
+        rows = _np(env.export_state())
+        o, m, r, te, ib = _np(obs), _np(info["action_mask"]), _np(rew), _np(term), _np(info["info_bits"])
+        for i, g in enumerate(games):
+            if active[i]:
+                assert digest(o[i], m[i], rows[i], r[i], te[i], int(ib[i])) == g["digests"][t], (g["seed"], g["policy"], t)
+    rows = _np(env.export_state())
+    for i, g in enumerate(games):
+        assert int(rows[i][72]) == g["moves"]
+        assert (None if rows[i][74] < 0 else int(rows[i][74])) == g["winner"]
+
+
+def test_philox_mode_rollout(VecEnv, oracle):
+    """Native Philox shuffles are not bit-equal to the reference's MT19937 decks, so the oracle is fed the
+    GPU's dealt state (replay of deck permutations) at every reset; everything else must be bit-exact."""
+    n, steps = 2048, 220
+    env = VecEnv(n, seed=99, shuffle="philox", autoreset=True)
+    obs, info = env.reset()
+    rows = _np(env.export_state())
+    # a valid deal: every card exactly once across board + decks, 3 distinct nobles, fresh counters
+    for i in range(0, n, 97):
+        r = rows[i]
+        cards = list(r[52:64]) + list(r[76:76 + r[64]]) + list(r[116:116 + r[65]]) + list(r[146:146 + r[66]])
+        assert sorted(cards) == list(range(90)) and (r[64], r[65], r[66]) == (36, 26, 16)
+        assert all(0 <= c < 40 for c in r[52:56]) and all(40 <= c < 70 for c in r[56:60]) and all(70 <= c < 90 for c in r[60:64])
+        assert len(set(r[67:70])) == 3 and all(0 <= x < 10 for x in r[67:70])
+    assert len({tuple(r[52:64]) for r in rows}) > n * 0.99  # decks differ across envs
+    ref = oracle.OracleVec(n)
+    ref.import_rows(rows)
+    robs, rmask = ref.observe()
+    assert np.array_equal(_np(obs), robs) and np.array_equal(_np(info["action_mask"]), rmask)
+    actions = env.sample_random_actions().clone()
+    resets = 0
+    for t in range(steps):
+        a = _np(actions).copy()
+        obs, rew, term, trunc, info = env.step(actions, sample_next=True)
+        robs, rrew, rterm, rinfo, rmask = (x.copy() for x in ref.step(a, autoreset=False))
+        assert np.array_equal(_np(rew), rrew) and np.array_equal(_np(term).astype(np.uint8), rterm)
+        ib = _np(info["info_bits"])
+        assert np.array_equal(ib & 0x7F, rinfo)
+        was_reset = (ib & 128) != 0
+        assert np.array_equal(was_reset, rterm != 0)
+        if was_reset.any():
+            rows = _np(env.export_state())
+            assert (rows[was_reset][:, 72] == 0).all()
+            ref.import_rows(rows, which=was_reset.astype(np.uint8))
+            o2, m2 = ref.observe()
+            robs[was_reset], rmask[was_reset] = o2[was_reset], m2[was_reset]
+            resets += int(was_reset.sum())
+        assert np.array_equal(_np(obs), robs), f"step {t}"
+        assert np.array_equal(_np(info["action_mask"]), rmask), f"step {t}"
+        actions = env.next_action.clone()
+    assert resets > n
+    assert np.array_equal(_np(env.export_state()), ref.export_rows())
+
+
+def test_philox_deals_are_uniform(VecEnv):
+    """First-slot card of each tier and first noble should be uniform over 40/30/20/10 values."""
+    n = 65536
+    env = VecEnv(n, seed=3, shuffle="philox")
+    env.reset()
+    rows = _np(env.export_state())
+    for col, lo, k in ((52, 0, 40), (56, 40, 30), (60, 70, 20), (67, 0, 10), (76 + 35, 0, 40)):
+        counts = np.bincount(rows[:, col] - lo, minlength=k)
+        expected = n / k
+        chi2 = ((counts - expected) ** 2 / expected).sum()
+        assert chi2 < 3.0 * k, (col, chi2)  # dof = k-1; 3x is far beyond the 1e-6 tail
+
+
+def test_active_mask_and_observe(VecEnv, oracle):
+    n = 777
+    env = VecEnv(n, seed=5, shuffle="mt19937", autoreset=False)
+    env.reset()
+    ref = oracle.OracleVec(n, seed_base=5)
+    ref.reset()
+    rng = np.random.RandomState(0)
+    for t in range(60):
+        a = ref.random_actions(1, t)
+        active = rng.rand(n) < 0.6
+        out = env.step(torch.from_numpy(a).cuda(), active=torch.from_numpy(active).cuda())
+        robs, rrew, rterm, rinfo, rmask = ref.step(a, active=active.astype(np.uint8), autoreset=False)
+        rrew, rterm, rinfo = rrew.copy(), rterm.copy(), rinfo.copy()
+        rrew[~active], rterm[~active], rinfo[~active] = 0, 0, 0
+        o2, m2 = ref.observe()
+        assert_step_equal(env, out, (o2, rrew, rterm, rinfo, m2), t, check_state=ref.export_rows())
+    o, m = env.observe()
+    o2, m2 = ref.observe()
+    assert np.array_equal(_np(o), o2) and np.array_equal(_np(m), m2)
+
+
+def test_random_action_kernel_matches_oracle_stream(VecEnv, oracle):
+    n = 1000
+    env = VecEnv(n, seed=11, shuffle="mt19937")
+    env.reset()
+    ref = oracle.OracleVec(n, seed_base=11)
+    ref.reset()
+    got = _np(env.sample_random_actions())
+    assert np.array_equal(got, ref.random_actions(env.action_key, 0))
+    m = _np(env.mask)
+    assert (m[np.arange(n), got] == 1).all()
+    zero = torch.zeros((n, 45), dtype=torch.int8, device="cuda")
+    assert (_np(env.sample_random_actions(mask=zero)) == 0).all()
+
+
+def test_dual_step_matches_two_reference_steps(VecEnv, oracle):
+    """DualStepNativeWrapper.dual_step = env.step(agent) -> opponent policy -> env.step(opponent)
+    (wrappers/dual_step_native.py:90-193) with the reward bookkeeping of :132-167."""
+    n = 1024
+    env = VecEnv(n, seed=77, shuffle="mt19937", autoreset=True)
+    ref = oracle.OracleVec(n, seed_base=77)
+    env.reset()
+    ref.reset()
+    t = [0]
+
+    def opp_policy(obs, mask):
+        return env.sample_random_actions(mask)
+
+    dones = 0
+    for it in range(150):
+        a = env.sample_random_actions().clone()
+        a_np = _np(a).copy()
+        agent_obs, agent_r, opp_obs, opp_r, done, info = env.dual_step(a, opp_policy)
+        # oracle: two single steps with the same actions
+        _, r1, t1, i1, _ = (x.copy() for x in ref.step(a_np, autoreset=True))
+        active = (t1 == 0) & ((i1 & 65) == 0)
+        opp_a = ref.random_actions(env.action_key, env._t - 1)
+        robs, r2, t2, i2, rmask = (x.copy() for x in ref.step(opp_a, active=active.astype(np.uint8), autoreset=True))
+        robs, rmask = ref.observe()
+        w2 = ((i2 >> 4) & 3).astype(int) - 1
+        fr0 = np.where(w2 < 0, np.where(i2 & 4, -0.1, 0.0), np.where(w2 == 0, 1.0, -1.0)).astype(np.float32)
+        fr0 = np.where((t2 != 0) & ((i2 & 2) == 0), fr0, 0.0).astype(np.float32)
+        w1 = ((i1 >> 4) & 3).astype(int) - 1
+        fr1 = np.where(w1 < 0, np.where(i1 & 4, -0.1, 0.0), np.where(w1 == 1, 1.0, -1.0)).astype(np.float32)
+        fr1 = np.where((t1 != 0) & ((i1 & 2) == 0), fr1, 0.0).astype(np.float32)
+        want_agent = np.where(t1 != 0, r1, np.where(active, np.where(t2 != 0, fr0, 0.0), r1)).astype(np.float32)
+        want_opp = np.where(t1 != 0, fr1, np.where(active, r2, 0.0)).astype(np.float32)
+        want_done = (t1 != 0) | (active & (t2 != 0))
+        assert np.array_equal(_np(agent_r), want_agent) and np.array_equal(_np(opp_r), want_opp)
+        assert np.array_equal(_np(done), want_done)
+        assert np.array_equal(_np(agent_obs), robs) and np.array_equal(_np(info["action_mask"]), rmask)
+        assert (_np(agent_obs)[:, 294] == 0).all()  # agent (player 0) to move again
+        dones += int(want_done.sum())
+    assert dones > 500
+
+
+def test_full_size_invariants(VecEnv):
+    """BASELINE config sizes (65,536 and 1,048,576 envs): size-independent properties after a rollout --
+    token conservation per colour, hand limit, observation/mask/state consistency through spl_observe."""
+    for n in (65536, 1 << 20):
+        env = VecEnv(n, seed=1, shuffle="philox", autoreset=True)
+        env.reset()
+        actions = env.sample_random_actions()
+        for t in range(48):
+            obs, rew, term, trunc, info = env.step(actions, sample_next=True)
+            actions = env.next_action
+        obs = env.obs
+        total = obs[:, 0:6] + obs[:, 6:12] + obs[:, 19:25]
+        want = torch.tensor([4, 4, 4, 4, 4, 5], dtype=torch.int32, device=obs.device)
+        assert bool((total == want).all())
+        assert int(obs[:, 6:12].sum(dim=1).max()) <= 10 and int(obs[:, 19:25].sum(dim=1).max()) <= 10
+        assert int(obs.min()) >= 0 and int(obs[:, 296].max()) == 0  # auto-reset: never left terminal
+        o1, m1 = obs.clone(), env.mask.clone()
+        o2, m2 = env.observe()
+        assert torch.equal(o1, o2) and torch.equal(m1, m2)
+        assert bool((m1.sum(dim=1) > 0).all())
+        # every sampled action is legal under the returned mask
+        assert bool((m1.gather(1, env.next_action.long().view(-1, 1)) == 1).all())
+        assert int(env.stats[0]) > 0
+        del env
+        torch.cuda.empty_cache()
+
+
+def test_full_size_sampled_parity(VecEnv, oracle):
+    """65,536 envs x 96 lock-steps bit-exact against the oracle (every env, every step: obs + mask checksum
+    on device, full compare on a strided sample)."""
+    n, steps = 65536, 96
+    env = VecEnv(n, seed=42, shuffle="mt19937", autoreset=True)
+    ref = oracle.OracleVec(n, seed_base=42)
+    env.reset()
+    ref.reset()
+    actions = env.sample_random_actions().clone()
+    for t in range(steps):
+        a = _np(actions)
+        out = env.step(actions, sample_next=True)
+        ref_out = ref.step(a, autoreset=True)
+        assert_step_equal(env, out, ref_out, t)
+        actions = env.next_action.clone()
+    assert np.array_equal(_np(env.export_state()), ref.export_rows())
+    assert np.array_equal(_np(env.stats), ref.stats())
