@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--no-obs", action="store_true", help="config 4: mask + step only (no observation encode)")
     ap.add_argument("--shuffle", default="philox", choices=["philox", "mt19937"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "lockstep"],
+                    help="rollout: one persistent kernel per segment; lockstep: one spl_step launch per lock-step")
+    ap.add_argument("--skip-lockstep", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -65,7 +68,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -200,8 +203,8 @@ def run_b200(args):
     env.reset()
     env.sample_random_actions(out=act_buf[0])
 
-    def segment():
-        """T lock-steps into the rollout buffer; the actions for step t+1 are sampled by step t's kernel."""
+    def segment_lockstep():
+        """T lock-steps, one spl_step launch each; the actions for step t+1 are sampled by step t's kernel."""
         for t in range(T):
             env._t = t
             env.step(act_buf[t], out_obs=(obs_buf[t] if write_obs else None), out_mask=mask_buf[t], out_reward=rew_buf[t],
@@ -209,22 +212,39 @@ def run_b200(args):
         act_buf[0].copy_(act_buf[T])
         env.t_base += T
 
+    def segment_rollout():
+        """The same T lock-steps in ONE launch of the persistent rollout kernel (state stays in registers)."""
+        env._t = 0
+        env.rollout_random(T, act_buf[0], obs=obs_buf, mask=mask_buf, reward=rew_buf, terminated=term_buf, next_actions=act_buf)
+        act_buf[0].copy_(act_buf[T])
+        env.t_base += T
+
+    use_rollout = args.mode == "rollout" and args.shuffle == "philox"
+    segment = segment_rollout if use_rollout else segment_lockstep
     launches0 = lib.spl_launch_count()
     segment()  # eager once (also validates arguments)
     torch.cuda.synchronize()
     launches_per_segment = lib.spl_launch_count() - launches0
+
+    def make_graph(fn):
+        s_ = torch.cuda.Stream()
+        s_.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s_):
+            fn()
+        torch.cuda.current_stream().wait_stream(s_)
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_):
+            fn()
+        return g_
+
     graph = None
-    if not args.no_graph:
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            segment()
-        torch.cuda.current_stream().wait_stream(s)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            segment()
+    if not use_rollout and not args.no_graph:
+        graph = make_graph(segment_lockstep)
     run = graph.replay if graph is not None else segment
 
+    import ctypes as C
+
+    peak, peak_src = peaks()
     stats_host = torch.zeros(8, dtype=torch.int64, device=dev)
     for _ in range(W):
         run()
@@ -232,6 +252,9 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    live_timing = graph is None  # events around the dominant kernel, recorded on the launching stream in the timed region
+    if live_timing:
+        L.check(lib.spl_timing_enable(1))
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -243,43 +266,74 @@ def run_b200(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    tot, cnt = C.c_double(), C.c_int64()
+    if live_timing:
+        L.check(lib.spl_timing_read(C.byref(tot), C.byref(cnt)))
+        L.check(lib.spl_timing_enable(0))
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
-    clocks = sampler.stop() if sampler else None
     total_steps = N * T * K * world
     value = total_steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel: CUDA events recorded by the library around every step-kernel launch
-    peak, peak_src = peaks()
-    L.check(lib.spl_timing_enable(1))
-    reps = max(1, min(K, 4096 // T))
-    for _ in range(reps):
-        segment()
-    import ctypes as C
-
-    tot, cnt = C.c_double(), C.c_int64()
-    L.check(lib.spl_timing_read(C.byref(tot), C.byref(cnt)))
-    L.check(lib.spl_timing_enable(0))
-    bytes_per_unit = B_FULL if write_obs else B_MASKSTEP
+    # ---- roofline of the dominant kernel
+    if not live_timing:  # graph replays cannot carry the library's events: time eager launches of the same kernel
+        L.check(lib.spl_timing_enable(1))
+        for _ in range(max(1, min(K, 4096 // T))):
+            segment()
+        L.check(lib.spl_timing_read(C.byref(tot), C.byref(cnt)))
+        L.check(lib.spl_timing_enable(0))
+    clocks = sampler.stop() if sampler else None
+    out_bytes = (1188 if write_obs else 0) + 45 + 4 + 1 + 4  # obs + mask + reward + terminated + action, per env-step
+    if use_rollout:
+        kernel = "spl_rollout_kernel"
+        units_per_launch = N * T
+        bytes_per_launch = N * T * out_bytes + N * 128 + N * 4  # + packed state read once / written once + first actions
+    else:
+        kernel = "spl_step_kernel<true>"
+        units_per_launch = N
+        bytes_per_launch = N * (out_bytes + 128 + 4 + 1)  # + state read + write, action read, info byte
     k_ms = tot.value / max(1, cnt.value)
-    achieved = N * bytes_per_unit / (k_ms * 1e-3) / 1e9
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
+    survey_bytes = B_FULL if write_obs else B_MASKSTEP
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "spl_step_kernel<true>", "kernel_ms": k_ms, "launches_timed": cnt.value,
-                "algorithmic_bytes_per_env_step": bytes_per_unit, "peak_source": peak_src}
+                "kernel": kernel, "kernel_ms": k_ms, "launches_timed": cnt.value, "env_steps_per_launch": units_per_launch,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "algorithmic_bytes_per_env_step": bytes_per_launch / units_per_launch,
+                "survey_8d_bytes_per_env_step": survey_bytes,
+                "frac_with_survey_8d_bytes": units_per_launch * survey_bytes / (k_ms * 1e-3) / 1e9 / peak,
+                "peak_source": peak_src, "timed": "live in the timed region" if live_timing else "eager re-run after the graph-timed region"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
             with open(prof) as f:
                 tj = json.load(f)
-            key = f"{N}"
+            key = f"{kernel}:{N}:{T}"
             if key in tj:
                 roofline["traffic"] = tj[key]["dram_bytes_per_launch"]
                 roofline["traffic_source"] = tj[key].get("source")
         except Exception:
             pass
+
+    # ---- secondary: the same segment as T separate spl_step launches (policy-in-the-loop path), CUDA graph
+    lockstep = None
+    if use_rollout and not args.skip_lockstep:
+        g2 = make_graph(segment_lockstep)
+        for _ in range(2):
+            g2.replay()
+        k2 = max(2, min(K, 5))
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(k2):
+            g2.replay()
+        b1.record()
+        torch.cuda.synchronize()
+        lms = b0.elapsed_time(b1)
+        lockstep = {"value": N * T * k2 / (lms * 1e-3), "unit": UNIT, "what": "per-GPU, one spl_step launch per lock-step (CUDA graph of %d launches)" % T,
+                    "us_per_lock_step": 1e3 * lms / (k2 * T)}
+        del g2
 
     # ---- end-to-end through the public API with HOST buffers (H2D actions, D2H everything the reference's step returns)
     e2e = None
@@ -348,10 +402,11 @@ def run_b200(args):
                              % (N, "" if N == 65536 else "; envs overridden")) if write_obs else
                             "simplified take-3 rules, mask+step only (BASELINE configs[3]), %d envs per GPU" % N,
                 "envs_per_gpu": N, "lock_steps_per_step": T, "env_steps_per_step": N * T * world, "shuffle": args.shuffle,
+                "mode": "rollout kernel (1 launch per segment)" if use_rollout else "lockstep (1 launch per lock-step)",
                 "cuda_graph": graph is not None, "parallelism": f"env-sharded x{world}, no collective on the step path",
                 "l2": "rollout buffer %.1f GB per GPU is larger than the 126 MB L2; no flush" % (T * per_step_bytes / 1e9),
             },
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "lockstep": lockstep,
             "gpu_launches": int(launches_per_segment * K), "clocks": clocks,
             "episode_stats": dict(zip(L.STAT_NAMES, st)),
         }

@@ -131,6 +131,15 @@ int spl_reset(const spl_envs_t *envs, const uint64_t *seeds, const uint8_t *rese
  * legality check -> apply_action -> encode_observation -> legal_moves [-> same-step auto-reset]. */
 int spl_step(const spl_envs_t *envs, const spl_step_io_t *io, void *stream);
 
+/* `steps` lock-steps of uniform-random-legal play with same-step auto-reset in ONE launch -- the batched
+ * equivalent of scripts/random_rollout.py:13-30 (and of a random-policy rollout collection,
+ * ppo_splendor.py:219-297).  Outputs are step-major rollout buffers: obs [steps][n][297], mask
+ * [steps][n][45], reward / terminated / info [steps][n]; io->actions = actions of the first step [n];
+ * io->next_action = [steps+1][n] (row 0 is left untouched, row t+1 = action chosen after step t).
+ * Results are bit-identical to `steps` chained spl_step calls with action_t, action_t+1, ...
+ * Requires SPL_SHUFFLE_PHILOX and autoreset. */
+int spl_rollout_random(const spl_envs_t *envs, const spl_step_io_t *io, int32_t steps, void *stream);
+
 /* encode_observation (engine/encode.py:124-187) + legal_moves (engine/rules.py:40-93) of the current
  * states, without stepping (mask is all-zero for terminal states, as in envs/splendor_env.py:81). */
 int spl_observe(const spl_envs_t *envs, int32_t *obs, int8_t *mask, void *stream);

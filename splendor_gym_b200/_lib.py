@@ -35,7 +35,7 @@ STAT_NAMES = ("episodes", "p0_wins", "p1_wins", "tie_draws", "limit_draws", "nol
 EXPORTS = (
     "spl_init", "spl_reset", "spl_step", "spl_observe", "spl_random_action", "spl_export_state", "spl_import_state",
     "spl_dual_combine", "spl_error_string", "spl_version", "spl_host_ret_table", "spl_launch_count",
-    "spl_timing_enable", "spl_timing_read",
+    "spl_timing_enable", "spl_timing_read", "spl_rollout_random",
 )
 
 
@@ -85,6 +85,8 @@ def load():
     L.spl_reset.argtypes = [C.POINTER(SplEnvs), vp, vp, vp, vp, vp]
     L.spl_step.restype = C.c_int
     L.spl_step.argtypes = [C.POINTER(SplEnvs), C.POINTER(SplStepIO), vp]
+    L.spl_rollout_random.restype = C.c_int
+    L.spl_rollout_random.argtypes = [C.POINTER(SplEnvs), C.POINTER(SplStepIO), C.c_int32, vp]
     L.spl_observe.restype = C.c_int
     L.spl_observe.argtypes = [C.POINTER(SplEnvs), vp, vp, vp]
     L.spl_random_action.restype = C.c_int

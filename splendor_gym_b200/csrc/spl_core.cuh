@@ -356,10 +356,13 @@ SPL_HD void spl_enforce_token_limit(SplState& s, uint32_t tp, uint32_t turn, con
 	if (total <= 10) return;
 	uint32_t remaining = total - 10;
 	uint32_t bank_sum = spl_sum6(s.bank);
-	uint64_t stream;
-	uint32_t pos = 0, blk = 0;
-	uint64_t seed = 0;
-	bool tabulated = (turn - 1u < 99u) && (total - 11u < 3u) && (bank_sum < 15u);
+	// 21 three-bit draws per 64-bit block; block 0 of every seed reachable in legitimate play is tabulated,
+	// anything else (hand-built states, or > 21 draws) is recomputed by spl_mt_top3_block -- one call site.
+	const uint64_t seed = ((uint64_t)turn * 1315423911ull) ^ ((uint64_t)tp * 2654435761ull) ^ ((uint64_t)total * 97531ull) ^
+	                      ((uint64_t)bank_sum * 31337ull);
+	const bool tabulated = (turn - 1u < 99u) && (total - 11u < 3u) && (bank_sum < 15u);
+	uint64_t stream = 0;
+	uint32_t pos = 21, next_blk = 0;
 	if (tabulated) {
 		uint32_t idx = (((turn - 1u) * 2u + tp) * 3u + (total - 11u)) * 15u + bank_sum;
 #if defined(__CUDA_ARCH__)
@@ -367,10 +370,8 @@ SPL_HD void spl_enforce_token_limit(SplState& s, uint32_t tp, uint32_t turn, con
 #else
 		stream = ret_table[idx];
 #endif
-	} else {
-		seed = ((uint64_t)turn * 1315423911ull) ^ ((uint64_t)tp * 2654435761ull) ^ ((uint64_t)total * 97531ull) ^
-		       ((uint64_t)bank_sum * 31337ull);
-		stream = spl_mt_top3_block(seed, 0);
+		pos = 0;
+		next_blk = 1;
 	}
 	while (remaining > 0) {
 		uint32_t choices = spl_colours_ge(s.tok[0], 1);  // ascending colour order (:170)
@@ -380,17 +381,11 @@ SPL_HD void spl_enforce_token_limit(SplState& s, uint32_t tp, uint32_t turn, con
 		uint32_t r;
 		do {  // Lib/random.py _randbelow_with_getrandbits
 			if (pos == 21) {
-				if (tabulated) {  // cannot happen (<= 18 outputs in the tabulated domain), kept for safety
-					seed = ((uint64_t)turn * 1315423911ull) ^ ((uint64_t)tp * 2654435761ull) ^
-					       ((uint64_t)total * 97531ull) ^ ((uint64_t)bank_sum * 31337ull);
-					tabulated = false;
-				}
-				blk++;
-				if (blk > 9) {  // > 210 MT outputs: outside what the O(1)-storage restatement covers
+				if (next_blk > 9) {  // > 210 MT outputs: outside what the O(1)-storage restatement covers
 					err = 1;
 					return;
 				}
-				stream = spl_mt_top3_block(seed, blk);
+				stream = spl_mt_top3_block(seed, next_blk++);
 				pos = 0;
 			}
 			r = ((uint32_t)(stream >> (3 * pos)) & 7u) >> drop;
@@ -491,7 +486,11 @@ SPL_HD void spl_env_step(SplState& s, int32_t action, const uint8_t* deck, const
 		uint32_t dn = (s.deckn >> (8 * pop_tier)) & 0xFFu;
 		if (dn > 0) {
 			uint32_t off = pop_tier == 0 ? 0u : (pop_tier == 1 ? 40u : 70u);
+#if defined(__CUDA_ARCH__)
+			popped = __ldcg(deck + off + dn - 1);  // L2-coherent: the row may have been written by other lanes (fused reset)
+#else
 			popped = deck[off + dn - 1];
+#endif
 			s.deckn -= 1u << (8 * pop_tier);
 		}
 	}

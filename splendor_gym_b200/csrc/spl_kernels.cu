@@ -93,8 +93,7 @@ __device__ __forceinline__ void spl_store_mask_tile(int8_t* gtile, uint64_t m, i
 		if (byte0 + 16 <= tile_bytes) {
 			__stcs(reinterpret_cast<int4*>(gtile) + q, v);
 		} else if (byte0 < tile_bytes) {  // ragged last tile
-			const int8_t* b = reinterpret_cast<const int8_t*>(&v);
-			for (int j = 0; byte0 + j < tile_bytes; j++) gtile[byte0 + j] = b[j];
+			for (int j = 0; j < 16 && byte0 + j < tile_bytes; j++) gtile[byte0 + j] = (int8_t)((bits >> j) & 1u);
 		}
 	}
 }
@@ -138,15 +137,95 @@ __device__ __forceinline__ void spl_store_obs_tile(int32_t* gtile, const uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
-// step / observe kernel
+// Native (Philox) deal: a uniformly random permutation of each deck and of the nobles by SORTING
+// RANDOM KEYS, done by the whole warp for ONE environment (the rest of the warp would otherwise idle
+// while a single lane ran a 100-step Fisher-Yates).  Element e (cards 0..89, nobles 90..99) gets the key
+// philox4x32-10(ctr = {e/4, env_lo, env_hi, episode}, key = seed)[e%4]; its position in its deck is the
+// rank of (key, e) among the elements of the same tier.  The deal is a pure function of
+// (seed, global env id, episode), so it does not depend on the GPU count or on which kernel performs it.
+// `scratch` = >= 132 words of shared memory private to the warp.  Writes the 96-byte deck row to `gdeck`.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void spl_coop_deal(uint64_t seed, uint64_t genv, uint32_t episode, uint32_t* scratch, int lane,
+                                              uint8_t* gdeck, uint32_t board[3], uint32_t& nobles) {
+	uint32_t* keys = scratch;                                      // [100] (+4 pad)
+	uint8_t* sdeck = reinterpret_cast<uint8_t*>(scratch + 104);    // [96]
+	uint8_t* snob = reinterpret_cast<uint8_t*>(scratch + 128);     // [10] (+pad)
+	if (lane < 25) {
+		uint4 c = spl_philox(make_uint4((uint32_t)lane, (uint32_t)genv, (uint32_t)(genv >> 32), episode), (uint32_t)seed,
+		                     (uint32_t)(seed >> 32));
+		*reinterpret_cast<uint4*>(keys + 4 * lane) = c;
+	}
+	if (lane < 24) reinterpret_cast<uint32_t*>(sdeck)[lane] = 0xFFFFFFFFu;
+	__syncwarp();
+	{  // tier 1: elements 0..39, two per lane for lanes 0..7
+		const uint32_t e0 = lane, e1 = 32 + lane;
+		const uint32_t k0 = keys[e0], k1 = keys[e1 < 40 ? e1 : 0];
+		uint32_t r0 = 0, r1 = 0;
+#pragma unroll 8
+		for (uint32_t i = 0; i < 40; i++) {
+			uint32_t ki = keys[i];
+			r0 += (ki < k0) || (ki == k0 && i < e0);
+			r1 += (ki < k1) || (ki == k1 && i < e1);
+		}
+		sdeck[r0] = (uint8_t)e0;
+		if (lane < 8) sdeck[r1] = (uint8_t)e1;
+	}
+	{  // tier 2: elements 40..69 | tier 3: 70..89 | nobles: 90..99 -- one element per lane each
+		const uint32_t e2 = 40 + lane, e3 = 70 + lane, e4 = 90 + lane;
+		const uint32_t k2 = keys[lane < 30 ? e2 : 40], k3 = keys[lane < 20 ? e3 : 70], k4 = keys[lane < 10 ? e4 : 90];
+		uint32_t r2 = 0, r3 = 0, r4 = 0;
+#pragma unroll 6
+		for (uint32_t i = 40; i < 70; i++) {
+			uint32_t ki = keys[i];
+			r2 += (ki < k2) || (ki == k2 && i < e2);
+		}
+#pragma unroll 5
+		for (uint32_t i = 70; i < 90; i++) {
+			uint32_t ki = keys[i];
+			r3 += (ki < k3) || (ki == k3 && i < e3);
+		}
+#pragma unroll
+		for (uint32_t i = 90; i < 100; i++) {
+			uint32_t ki = keys[i];
+			r4 += (ki < k4) || (ki == k4 && i < e4);
+		}
+		if (lane < 30) sdeck[40 + r2] = (uint8_t)e2;
+		if (lane < 20) sdeck[70 + r3] = (uint8_t)e3;
+		if (lane < 10) snob[r4] = (uint8_t)lane;
+	}
+	__syncwarp();
+	// deal four cards per tier by pop() from the END of the deck (engine/state.py:190-191); first three nobles (:194-195)
+	const uint32_t* d32 = reinterpret_cast<const uint32_t*>(sdeck);
+	board[0] = __byte_perm(d32[9], 0, 0x0123);                          // deck1[39],[38],[37],[36]
+	board[1] = __byte_perm(d32[16], d32[17], 0x2345);                   // deck2 = bytes 40..69: [69],[68],[67],[66]
+	board[2] = __byte_perm(d32[21], d32[22], 0x2345);                   // deck3 = bytes 70..89: [89],[88],[87],[86]
+	nobles = (uint32_t)snob[0] | ((uint32_t)snob[1] << 8) | ((uint32_t)snob[2] << 16);
+	if (lane < 24) reinterpret_cast<uint32_t*>(gdeck)[lane] = d32[lane];
+	__syncwarp();
+}
+
+__device__ __forceinline__ void spl_state_from_deal(SplState& s, const uint32_t board[3], uint32_t nobles) {
+	spl_fresh_state(s);
+	s.board[0] = board[0], s.board[1] = board[1], s.board[2] = board[2];
+	s.deckn = 36u | (26u << 8) | (16u << 16);
+	s.nobles = nobles;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step / observe / rollout kernels
+// ------------------------------------------------------------------------------------------------
+#define SPL_RESET_NONE 0
+#define SPL_RESET_WORKLIST 1 /* queue finished envs for spl_reset_kernel (MT19937 shuffles need 2.5 KB of state per env) */
+#define SPL_RESET_FUSED 2    /* deal the new episode right here (Philox) */
+
 struct StepParams {
 	uint4* state;
 	int64_t stride;
-	const uint8_t* decks;
+	uint8_t* decks;
+	uint32_t* episode;
 	int32_t* scratch;
 	int64_t n;
-	uint64_t env_offset;
+	uint64_t env_offset, seed_base;
 	const int32_t* actions;
 	const uint8_t* active;
 	int32_t* obs;
@@ -158,111 +237,203 @@ struct StepParams {
 	int32_t* next_action;
 	uint64_t action_key, action_t;
 	const uint64_t* action_t_base;
-	int autoreset;
+	int reset_mode;
 	int vec_ok;  // obs / mask bases are 16-byte aligned
+	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
 };
 
+struct SplTile {
+	const SplTables* T;
+	uint32_t* smem;  // SPL_TILE_WORDS words private to the warp
+	int lane;
+	int64_t ti;      // tile index; env = ti*32 + lane
+	int rows;        // valid envs in the tile
+};
+
+// one SplendorEnv.step for the lane's env + episode statistics + same-step auto-reset
+__device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile& tl, SplState& s, bool act, int32_t action, int64_t env,
+                                              SplStepResult& r) {
+	const int lane = tl.lane;
+	r.reward = 0.0f, r.terminated = 0, r.info = 0;
+	if (act) spl_env_step(s, action, p.decks + env * SPL_DECK_STRIDE, tl.T, g_ret_table, r);
+	const bool finished = r.terminated && !(r.info & SPL_INFO_ERROR);
+	const bool do_reset = act && r.terminated && p.reset_mode != SPL_RESET_NONE;
+	if (do_reset) r.info |= SPL_INFO_RESET;
+	// episode statistics: warp-reduce, one atomic per counter per warp
+	if (p.stats != nullptr && __any_sync(SPL_FULL, finished)) {
+		uint32_t wcode = (s.flags & SPL_FLAG_WINNER_MASK) >> SPL_FLAG_WINNER_SHIFT;
+		bool nolegal = r.info & SPL_INFO_NOLEGAL_DRAW, limit = r.info & SPL_INFO_TURN_LIMIT;
+		uint32_t v[8];
+		v[SPL_STAT_EPISODES] = finished;
+		v[SPL_STAT_NOLEGAL_DRAWS] = finished && nolegal;
+		v[SPL_STAT_LIMIT_DRAWS] = finished && !nolegal && limit;
+		v[SPL_STAT_P0_WINS] = finished && !nolegal && !limit && wcode == 1;
+		v[SPL_STAT_P1_WINS] = finished && !nolegal && !limit && wcode == 2;
+		v[SPL_STAT_TIE_DRAWS] = finished && !nolegal && !limit && wcode == 0;
+		v[SPL_STAT_SUM_MOVES] = finished ? s.move : 0u;
+		// terminal => to_play == 0 => perspective index == player index
+		v[SPL_STAT_SUM_WINNER_PRESTIGE] = (finished && wcode) ? (wcode == 1 ? s.prestige[0] : s.prestige[1]) : 0u;
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			uint32_t tot = __reduce_add_sync(SPL_FULL, v[k]);
+			if (lane == 0 && tot) atomicAdd(p.stats + k, (unsigned long long)tot);
+		}
+	}
+	uint32_t rb = __ballot_sync(SPL_FULL, do_reset);
+	if (rb == 0) return;
+	if (p.reset_mode == SPL_RESET_WORKLIST) {
+		int base = 0;
+		if (lane == 0) base = atomicAdd(p.scratch, __popc(rb));
+		base = __shfl_sync(SPL_FULL, base, 0);
+		if (do_reset) p.scratch[4 + base + __popc(rb & ((1u << lane) - 1u))] = (int32_t)env;
+	} else {
+		while (rb) {  // warp-uniform loop over the lanes whose episode just ended
+			const int src = __ffs(rb) - 1;
+			rb &= rb - 1;
+			uint32_t ep = 0;
+			if (lane == src) {
+				ep = p.episode[env] + 1u;
+				p.episode[env] = ep;
+			}
+			ep = __shfl_sync(SPL_FULL, ep, src);
+			const int64_t e = __shfl_sync(SPL_FULL, env, src);
+			uint32_t board[3], nobles;
+			spl_coop_deal(p.seed_base, p.env_offset + (uint64_t)e, ep, tl.smem, lane, p.decks + e * SPL_DECK_STRIDE, board, nobles);
+			if (lane == src) spl_state_from_deal(s, board, nobles);
+		}
+	}
+}
+
+// outputs of the lane's (possibly new) state: legal mask tile, sampled next action, observation tile
+__device__ __forceinline__ int32_t spl_tile_emit(const StepParams& p, const SplTile& tl, const SplState& s, const uint32_t* w, int64_t env,
+                                                 bool valid, int32_t* obs, int8_t* mask, int32_t* next_action, uint64_t t) {
+	const int lane = tl.lane;
+	// legal_moves of the resulting state (all-zero once terminal, envs/splendor_env.py:81)
+	uint64_t m = 0;
+	int32_t sampled = 0;
+	if (mask != nullptr || next_action != nullptr) m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, tl.T);
+	if (mask != nullptr) {
+		if (p.vec_ok) spl_store_mask_tile(mask + tl.ti * 32 * SPL_NUM_ACTIONS, m, lane, tl.rows);
+		else if (valid)
+			for (int a = 0; a < SPL_NUM_ACTIONS; a++) mask[env * SPL_NUM_ACTIONS + a] = (int8_t)((m >> a) & 1);
+	}
+	if (next_action != nullptr) {
+		sampled = spl_sample_action(m, p.action_key, p.env_offset + (uint64_t)env, t);
+		if (valid) next_action[env] = sampled;
+	}
+	if (obs != nullptr) {
+		SplObsStager stage(tl.smem, lane, w[0]);
+		spl_encode_observation(w, s, tl.T, stage);
+		__syncwarp();
+		spl_store_obs_tile(obs + tl.ti * 32 * SPL_OBS_DIM, tl.smem, lane, tl.rows, p.vec_ok);
+		__syncwarp();
+	}
+	return sampled;
+}
+
+__device__ __forceinline__ void spl_load_state(const StepParams& p, int64_t env, bool valid, uint32_t* w) {
+	if (valid) {
+#pragma unroll
+		for (int pl = 0; pl < SPL_STATE_PLANES; pl++) {
+			uint4 v = p.state[pl * p.stride + env];
+			w[4 * pl + 0] = v.x, w[4 * pl + 1] = v.y, w[4 * pl + 2] = v.z, w[4 * pl + 3] = v.w;
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < 16; k++) w[k] = 0;
+	}
+}
+
+__device__ __forceinline__ void spl_store_state(const StepParams& p, int64_t env, const uint32_t* w) {
+#pragma unroll
+	for (int pl = 0; pl < SPL_STATE_PLANES; pl++)
+		p.state[pl * p.stride + env] = make_uint4(w[4 * pl + 0], w[4 * pl + 1], w[4 * pl + 2], w[4 * pl + 3]);
+}
+
+__device__ __forceinline__ const SplTables* spl_stage_tables(SplTables* T) {
+	const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
+	uint32_t* dst = reinterpret_cast<uint32_t*>(T);
+	for (int i = threadIdx.x; i < (int)(sizeof(SplTables) / 4); i += blockDim.x) dst[i] = src[i];
+	__syncthreads();
+	return T;
+}
+
+// one lock-step (DO_STEP) or just encode_observation + legal_moves of the current states
 template <bool DO_STEP>
 __global__ void __launch_bounds__(SPL_WARPS_PER_CTA * 32) spl_step_kernel(const StepParams p) {
-	__shared__ SplTables T;
-	__shared__ uint32_t tiles[SPL_WARPS_PER_CTA][SPL_TILE_WORDS];
-	{
-		const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
-		uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
-		for (int i = threadIdx.x; i < (int)(sizeof(SplTables) / 4); i += blockDim.x) dst[i] = src[i];
-	}
-	__syncthreads();
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t* tile = tiles[warp];
+	__shared__ SplTables Ts;
+	__shared__ __align__(16) uint32_t tiles[SPL_WARPS_PER_CTA][SPL_TILE_WORDS];
+	SplTile tl;
+	tl.T = spl_stage_tables(&Ts);
+	tl.lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	tl.smem = tiles[warp];
 	const int64_t ntiles = (p.n + 31) >> 5;
+	const uint64_t t = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
 
-	for (int64_t ti = (int64_t)blockIdx.x * SPL_WARPS_PER_CTA + warp; ti < ntiles; ti += (int64_t)gridDim.x * SPL_WARPS_PER_CTA) {
-		const int64_t env = ti * 32 + lane;
+	for (tl.ti = (int64_t)blockIdx.x * SPL_WARPS_PER_CTA + warp; tl.ti < ntiles; tl.ti += (int64_t)gridDim.x * SPL_WARPS_PER_CTA) {
+		const int64_t env = tl.ti * 32 + tl.lane;
 		const bool valid = env < p.n;
-		const int rows = (int)min((int64_t)32, p.n - ti * 32);
+		tl.rows = (int)min((int64_t)32, p.n - tl.ti * 32);
 		uint32_t w[16];
-		if (valid) {
-#pragma unroll
-			for (int pl = 0; pl < SPL_STATE_PLANES; pl++) {
-				uint4 v = p.state[pl * p.stride + env];
-				w[4 * pl + 0] = v.x, w[4 * pl + 1] = v.y, w[4 * pl + 2] = v.z, w[4 * pl + 3] = v.w;
-			}
-		} else {
-#pragma unroll
-			for (int k = 0; k < 16; k++) w[k] = 0;
-		}
+		spl_load_state(p, env, valid, w);
 		SplState s;
 		spl_unpack(w, s);
-
 		if (DO_STEP) {
 			const bool act = valid && (p.active == nullptr || p.active[env] != 0);
 			SplStepResult r;
-			r.reward = 0.0f, r.terminated = 0, r.info = 0;
+			spl_tile_step(p, tl, s, act, act ? p.actions[env] : 0, env, r);
 			if (act) {
-				spl_env_step(s, p.actions[env], p.decks + env * SPL_DECK_STRIDE, &T, g_ret_table, r);
 				spl_pack(s, w);
-#pragma unroll
-				for (int pl = 0; pl < SPL_STATE_PLANES; pl++)
-					p.state[pl * p.stride + env] = make_uint4(w[4 * pl + 0], w[4 * pl + 1], w[4 * pl + 2], w[4 * pl + 3]);
+				spl_store_state(p, env, w);
 			}
-			const bool finished = r.terminated && !(r.info & SPL_INFO_ERROR);
-			const bool do_reset = act && r.terminated && p.autoreset;
-			if (do_reset) r.info |= SPL_INFO_RESET;
 			if (valid) {
 				p.reward[env] = r.reward;
 				p.terminated[env] = (uint8_t)r.terminated;
 				p.info[env] = (uint8_t)r.info;
 			}
-			// episode statistics: warp-reduce, one atomic per counter per warp
-			if (p.stats != nullptr && __any_sync(SPL_FULL, finished)) {
-				uint32_t wcode = (s.flags & SPL_FLAG_WINNER_MASK) >> SPL_FLAG_WINNER_SHIFT;
-				bool nolegal = r.info & SPL_INFO_NOLEGAL_DRAW, limit = r.info & SPL_INFO_TURN_LIMIT;
-				uint32_t v[8];
-				v[SPL_STAT_EPISODES] = finished;
-				v[SPL_STAT_NOLEGAL_DRAWS] = finished && nolegal;
-				v[SPL_STAT_LIMIT_DRAWS] = finished && !nolegal && limit;
-				v[SPL_STAT_P0_WINS] = finished && !nolegal && !limit && wcode == 1;
-				v[SPL_STAT_P1_WINS] = finished && !nolegal && !limit && wcode == 2;
-				v[SPL_STAT_TIE_DRAWS] = finished && !nolegal && !limit && wcode == 0;
-				v[SPL_STAT_SUM_MOVES] = finished ? s.move : 0u;
-				// terminal => to_play == 0 => perspective index == player index
-				v[SPL_STAT_SUM_WINNER_PRESTIGE] = (finished && wcode) ? s.prestige[wcode - 1] : 0u;
-#pragma unroll
-				for (int k = 0; k < 8; k++) {
-					uint32_t tot = __reduce_add_sync(SPL_FULL, v[k]);
-					if (lane == 0 && tot) atomicAdd(p.stats + k, (unsigned long long)tot);
-				}
-			}
-			// same-step auto-reset: queue the env for the reset kernel that follows on the stream
-			uint32_t rb = __ballot_sync(SPL_FULL, do_reset);
-			if (rb) {
-				int base = 0;
-				if (lane == 0) base = atomicAdd(p.scratch, __popc(rb));
-				base = __shfl_sync(SPL_FULL, base, 0);
-				if (do_reset) p.scratch[4 + base + __popc(rb & ((1u << lane) - 1u))] = (int32_t)env;
-			}
 		}
+		spl_tile_emit(p, tl, s, w, env, valid, p.obs, p.mask, p.next_action, t);
+	}
+}
 
-		// legal_moves of the resulting state (all-zero once terminal, envs/splendor_env.py:81)
-		uint64_t m = 0;
-		if (p.mask != nullptr || p.next_action != nullptr) m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, &T);
-		if (p.mask != nullptr) {
-			if (p.vec_ok) spl_store_mask_tile(p.mask + ti * 32 * SPL_NUM_ACTIONS, m, lane, rows);
-			else if (valid)
-				for (int a = 0; a < SPL_NUM_ACTIONS; a++) p.mask[env * SPL_NUM_ACTIONS + a] = (int8_t)((m >> a) & 1);
-		}
-		if (p.next_action != nullptr && valid) {
-			uint64_t t = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
-			p.next_action[env] = spl_sample_action(m, p.action_key, p.env_offset + (uint64_t)env, t);
-		}
+// `steps` lock-steps of uniform-random-legal play with same-step auto-reset in ONE launch: every warp keeps its
+// 32 games in registers and streams each step's observation / mask / reward / terminated / action into
+// [steps][n][...] rollout buffers.  Bit-identical to `steps` calls of spl_step chained through next_action.
+__global__ void __launch_bounds__(SPL_WARPS_PER_CTA * 32) spl_rollout_kernel(const StepParams p) {
+	__shared__ SplTables Ts;
+	__shared__ __align__(16) uint32_t tiles[SPL_WARPS_PER_CTA][SPL_TILE_WORDS];
+	SplTile tl;
+	tl.T = spl_stage_tables(&Ts);
+	tl.lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	tl.smem = tiles[warp];
+	const int64_t ntiles = (p.n + 31) >> 5;
+	const uint64_t t0 = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
 
-		if (p.obs != nullptr) {
-			SplObsStager stage(tile, lane, w[0]);
-			spl_encode_observation(w, s, &T, stage);
-			__syncwarp();
-			spl_store_obs_tile(p.obs + ti * 32 * SPL_OBS_DIM, tile, lane, rows, p.vec_ok);
-			__syncwarp();
+	for (tl.ti = (int64_t)blockIdx.x * SPL_WARPS_PER_CTA + warp; tl.ti < ntiles; tl.ti += (int64_t)gridDim.x * SPL_WARPS_PER_CTA) {
+		const int64_t env = tl.ti * 32 + tl.lane;
+		const bool valid = env < p.n;
+		tl.rows = (int)min((int64_t)32, p.n - tl.ti * 32);
+		uint32_t w[16];
+		spl_load_state(p, env, valid, w);
+		SplState s;
+		spl_unpack(w, s);
+		int32_t action = valid ? p.actions[env] : 0;
+		for (int st = 0; st < p.steps; st++) {
+			const int64_t o = (int64_t)st * p.n;
+			SplStepResult r;
+			spl_tile_step(p, tl, s, valid, action, env, r);
+			spl_pack(s, w);
+			if (valid) {
+				p.reward[o + env] = r.reward;
+				p.terminated[o + env] = (uint8_t)r.terminated;
+				if (p.info != nullptr) p.info[o + env] = (uint8_t)r.info;
+			}
+			action = spl_tile_emit(p, tl, s, w, env, valid, p.obs ? p.obs + o * SPL_OBS_DIM : nullptr,
+			                       p.mask ? p.mask + o * SPL_NUM_ACTIONS : nullptr, p.next_action + o + p.n, t0 + (uint64_t)st);
 		}
+		if (valid) spl_store_state(p, env, w);
 	}
 }
 
@@ -420,32 +591,45 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 		uint8_t* deck = decks_s + lane * SPL_DECK_SMEM;
 		SplState s;
 		uint32_t w[16];
+		uint32_t ep = 0;
+		uint64_t seed = 0;
 		if (valid) {
-			uint32_t ep = p.bump_episode ? p.episode[env] + 1u : 0u;
+			ep = p.bump_episode ? p.episode[env] + 1u : 0u;
 			p.episode[env] = ep;
 			uint64_t genv = p.env_offset + (uint64_t)env;
-			uint64_t seed = p.seeds ? p.seeds[env] : (p.seed_base + 1000003ull * ep + genv) % 2147483647ull;
-			if (SHUFFLE == SPL_SHUFFLE_MT19937) {
+			seed = p.seeds ? p.seeds[env] : (p.seed_base + 1000003ull * ep + genv) % 2147483647ull;
+		}
+		spl_fresh_state(s);
+		if (SHUFFLE == SPL_SHUFFLE_MT19937) {
+			if (valid) {
 				SplMT rng;
 				rng.mt = mt_s + lane;
 				rng.seed(seed);
 				spl_deal(rng, deck, s);
-			} else {
-				SplPhiloxStream rng;
-				rng.init(p.seeds ? seed : p.seed_base, genv, ep);
-				spl_deal(rng, deck, s);
+				const uint32_t* d4 = reinterpret_cast<const uint32_t*>(deck);
+				uint32_t* g4 = reinterpret_cast<uint32_t*>(p.decks + env * SPL_DECK_STRIDE);
+#pragma unroll
+				for (int k = 0; k < SPL_DECK_STRIDE / 4; k++) g4[k] = d4[k];
 			}
-			spl_pack(s, w);
+		} else {
+			// same warp-cooperative deal as the fused auto-reset of the step kernel, one environment at a time
+			const uint32_t vb = __ballot_sync(SPL_FULL, valid);
+			for (uint32_t rb = vb; rb;) {
+				const int src = __ffs(rb) - 1;
+				rb &= rb - 1;
+				const int64_t e = __shfl_sync(SPL_FULL, env, src);
+				const uint32_t epr = __shfl_sync(SPL_FULL, ep, src);
+				const uint64_t key = p.seeds ? __shfl_sync(SPL_FULL, seed, src) : p.seed_base;
+				uint32_t board[3], nobles;
+				spl_coop_deal(key, p.env_offset + (uint64_t)e, epr, tile, lane, p.decks + e * SPL_DECK_STRIDE, board, nobles);
+				if (lane == src) spl_state_from_deal(s, board, nobles);
+			}
+		}
+		spl_pack(s, w);
+		if (valid) {
 #pragma unroll
 			for (int pl = 0; pl < SPL_STATE_PLANES; pl++)
 				p.state[pl * p.stride + env] = make_uint4(w[4 * pl + 0], w[4 * pl + 1], w[4 * pl + 2], w[4 * pl + 3]);
-			const uint32_t* d4 = reinterpret_cast<const uint32_t*>(deck);
-			uint32_t* g4 = reinterpret_cast<uint32_t*>(p.decks + env * SPL_DECK_STRIDE);
-#pragma unroll
-			for (int k = 0; k < SPL_DECK_STRIDE / 4; k++) g4[k] = d4[k];
-		} else {
-			spl_fresh_state(s);
-			spl_pack(s, w);
 		}
 		if (p.mask != nullptr || p.next_action != nullptr) {  // rows are scattered: one row per warp iteration, 45 coalesced bytes
 			uint64_t m = spl_legal_mask(s, T);
@@ -573,7 +757,7 @@ __global__ void spl_dual_combine_kernel(const float* r1, const uint8_t* t1, cons
 // ------------------------------------------------------------------------------------------------
 static int g_inited_device = -1;
 static int g_num_sms = 0;
-static int g_step_ctas_per_sm = 0, g_obs_ctas_per_sm = 0;
+static int g_step_ctas_per_sm = 0, g_obs_ctas_per_sm = 0, g_roll_ctas_per_sm = 0;
 static uint64_t g_host_ret[SPL_RET_TABLE_LEN];
 static bool g_host_ret_built = false;
 static int64_t g_launches = 0;
@@ -660,6 +844,9 @@ int spl_init(void) {
 	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_step_ctas_per_sm, spl_step_kernel<true>, SPL_WARPS_PER_CTA * 32, 0));
 	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_obs_ctas_per_sm, spl_step_kernel<false>, SPL_WARPS_PER_CTA * 32, 0));
+	SPL_CUDA(cudaFuncSetAttribute(spl_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_roll_ctas_per_sm, spl_rollout_kernel, SPL_WARPS_PER_CTA * 32, 0));
+	if (g_roll_ctas_per_sm < 1) g_roll_ctas_per_sm = 1;
 	if (g_step_ctas_per_sm < 1) g_step_ctas_per_sm = 1;
 	if (g_obs_ctas_per_sm < 1) g_obs_ctas_per_sm = 1;
 	SPL_CUDA(cudaDeviceSynchronize());
@@ -709,10 +896,9 @@ int spl_reset(const spl_envs_t* envs, const uint64_t* seeds, const uint8_t* rese
 	return launch_reset(envs, envs->scratch, seeds, 1, obs, mask, st);
 }
 
-static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, int32_t* obs, int8_t* mask, cudaStream_t st) {
-	StepParams p;
-	p.state = (uint4*)e->state, p.stride = e->stride, p.decks = e->decks, p.scratch = e->scratch, p.n = e->n;
-	p.env_offset = e->env_offset;
+static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_io_t* io, int32_t* obs, int8_t* mask) {
+	p.state = (uint4*)e->state, p.stride = e->stride, p.decks = e->decks, p.episode = e->episode, p.scratch = e->scratch;
+	p.n = e->n, p.env_offset = e->env_offset, p.seed_base = e->seed_base;
 	p.actions = io ? io->actions : nullptr, p.active = io ? io->active : nullptr;
 	p.obs = obs, p.mask = mask;
 	p.reward = io ? io->reward : nullptr, p.terminated = io ? io->terminated : nullptr, p.info = io ? io->info : nullptr;
@@ -720,11 +906,22 @@ static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 	p.next_action = io ? io->next_action : nullptr;
 	p.action_key = io ? io->action_key : 0, p.action_t = io ? io->action_t : 0;
 	p.action_t_base = io ? io->action_t_base : nullptr;
-	p.autoreset = io ? io->autoreset : 0;
+	p.reset_mode = SPL_RESET_NONE;
+	if (io && io->autoreset) p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED : SPL_RESET_WORKLIST;
 	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;
-	int64_t ctas = ((e->n + 31) / 32 + SPL_WARPS_PER_CTA - 1) / SPL_WARPS_PER_CTA;
-	int64_t cap = (int64_t)g_num_sms * (do_step ? g_step_ctas_per_sm : g_obs_ctas_per_sm);
-	int grid = (int)(ctas < cap ? ctas : cap);
+	p.steps = 1;
+}
+
+static int step_grid(int64_t n, int ctas_per_sm) {
+	int64_t ctas = ((n + 31) / 32 + SPL_WARPS_PER_CTA - 1) / SPL_WARPS_PER_CTA;
+	int64_t cap = (int64_t)g_num_sms * ctas_per_sm;
+	return (int)(ctas < cap ? ctas : cap);
+}
+
+static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, int32_t* obs, int8_t* mask, cudaStream_t st) {
+	StepParams p;
+	fill_step_params(p, e, io, obs, mask);
+	int grid = step_grid(e->n, do_step ? g_step_ctas_per_sm : g_obs_ctas_per_sm);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
 	if (do_step) spl_step_kernel<true><<<grid, SPL_WARPS_PER_CTA * 32, 0, st>>>(p);
@@ -739,15 +936,38 @@ int spl_step(const spl_envs_t* envs, const spl_step_io_t* io, void* stream) {
 	if (rc) return rc;
 	if (!io || !io->actions || !io->reward || !io->terminated || !io->info) return SPL_E_BADARG;
 	cudaStream_t st = (cudaStream_t)stream;
-	if (io->autoreset) SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, 16, st));
+	// Philox decks are dealt inside the step kernel; MT19937 decks (bit-exact with the reference) need the
+	// 624-word generator state per env, so finished envs are queued for the reset kernel that follows
+	const bool worklist = io->autoreset && envs->shuffle_mode != SPL_SHUFFLE_PHILOX;
+	if (worklist) SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, 16, st));
 	rc = launch_step(envs, io, true, io->obs, io->mask, st);
 	if (rc) return rc;
-	if (io->autoreset) {
+	if (worklist) {
 		// the reset kernel also re-samples next_action for the envs whose mask it replaces
 		rc = launch_reset(envs, envs->scratch, nullptr, 1, io->obs, io->mask, st, io);
 		if (rc) return rc;
 	}
 	return 0;
+}
+
+int spl_rollout_random(const spl_envs_t* envs, const spl_step_io_t* io, int32_t steps, void* stream) {
+	int rc = check_envs(envs);
+	if (rc) return rc;
+	if (!io || !io->actions || !io->reward || !io->terminated || !io->next_action || steps <= 0 || io->active) return SPL_E_BADARG;
+	if (envs->shuffle_mode != SPL_SHUFFLE_PHILOX || !io->autoreset) return SPL_E_BADARG;  // in-kernel resets need the native deal
+	StepParams p;
+	fill_step_params(p, envs, io, io->obs, io->mask);
+	p.steps = steps;
+	// every step's tile must stay 16-byte aligned: n*297*4 and n*45 are multiples of 16 iff n % 16 == 0
+	if (envs->n % 16 != 0) p.vec_ok = 0;
+	int grid = step_grid(envs->n, g_roll_ctas_per_sm);
+	cudaStream_t st = (cudaStream_t)stream;
+	const bool timed = g_timing && g_ev_used < SPL_TIMING_POOL;
+	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
+	spl_rollout_kernel<<<grid, SPL_WARPS_PER_CTA * 32, 0, st>>>(p);
+	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
+	g_launches++;
+	return (int)cudaGetLastError();
 }
 
 int spl_observe(const spl_envs_t* envs, int32_t* obs, int8_t* mask, void* stream) {

@@ -166,6 +166,32 @@ class SplendorVecEnv:
             return obs, reward, term.view(torch.bool), self.truncated, None
         return obs, self.reward, self.terminated, self.truncated, self.info()
 
+    def rollout_random(self, steps: int, actions: torch.Tensor, *, obs: Optional[torch.Tensor], mask: Optional[torch.Tensor],
+                       reward: torch.Tensor, terminated: torch.Tensor, next_actions: torch.Tensor,
+                       info: Optional[torch.Tensor] = None) -> None:
+        """``steps`` lock-steps of uniform-random-legal play (scripts/random_rollout.py:13-30, batched) with same-step
+        auto-reset in ONE kernel launch, streamed into step-major rollout buffers: ``obs [steps,N,297]``,
+        ``mask [steps,N,45]``, ``reward / terminated / info [steps,N]``, ``next_actions [steps+1,N]`` (row t+1 = the
+        action sampled after step t; row 0 is not written).  ``actions [N]`` are the actions of the first step.
+        Bit-identical to ``steps`` calls of ``step(..., sample_next=True)``.  Needs ``shuffle="philox"`` and autoreset."""
+        assert self._is_reset, "Call reset() first"
+        n = self.n
+        assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == n
+        assert next_actions.dtype == torch.int32 and next_actions.is_contiguous() and next_actions.numel() == (steps + 1) * n
+        assert reward.numel() == steps * n and terminated.numel() == steps * n
+        io = self._io
+        io.actions, io.active = actions.data_ptr(), None
+        io.obs, io.mask = _ptr(obs), _ptr(mask)
+        io.reward, io.terminated, io.info = reward.data_ptr(), terminated.data_ptr(), _ptr(info)
+        io.stats = self.stats.data_ptr()
+        io.next_action = next_actions.data_ptr()
+        io.action_key, io.action_t = self.action_key, self._t + 1
+        io.action_t_base = _ptr(self.t_base)
+        io.autoreset = 1
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_rollout_random(C.byref(self._envs), C.byref(io), int(steps), self._stream()), "spl_rollout_random")
+        self._t += steps
+
     def observe(self, out_obs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None):
         """encode_observation + legal_moves of the current states (no step)."""
         obs = self.obs if out_obs is None else out_obs
