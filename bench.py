@@ -35,8 +35,8 @@ UNIT = "env-steps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--rollout", type=int, default=128, help="lock-steps per bench step (ppo_splendor.py --num-steps)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -61,50 +61,101 @@ def peaks():
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML from a thread, ~1 kHz; nvidia-smi fallback)."""
 
     def __init__(self, index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+
+        self.samples, self.maxes, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        self._thread = None
+        self._smi = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+
+            nv.nvmlInit()
+            uuid = None
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+            except Exception:
+                pass
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(index)
+            self._nv, self._h = nv, h
+            self._max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
         except Exception:
-            self.p = None
+            self._thread = None
+            try:
+                self._f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self._smi = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                             stdout=self._f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self._smi = None
+
+    def _loop(self):
+        nv, h = self._nv, self._h
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
-                continue
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            if self.samples:
+                return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self._max, "reasons": sorted(self.reasons),
+                        "samples": len(self.samples), "source": "nvml"}
+        if self._smi is not None:
+            self._smi.terminate()
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
-        return out
+                self._smi.wait(timeout=5)
+            except Exception:
+                self._smi.kill()
+            self._f.flush()
+            self._f.seek(0)
+            sm, mx, reasons = [], [], set()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self._f.read().splitlines():
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            if sm:
+                return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
 
 
 # ------------------------------------------------------------------------------------------------- CPU legs

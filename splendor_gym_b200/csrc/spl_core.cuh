@@ -254,22 +254,20 @@ SPL_HD uint64_t spl_legal_mask(const SplState& s, const SplTables* T) {
 	m_lo |= spl_colours_ge(s.bank, 4) << 10;             // bits 10..14 (:61-63)
 	uint32_t wealth = spl_nib5_clamp7((s.tok[0] & 0xFFFFFFFFFFull) + s.bon[0]);
 	uint32_t gold = spl_byte(s.tok[0], 5);
-	uint32_t buy = 0, present = 0;
-#pragma unroll
-	for (int slot = 0; slot < 12; slot++) {              // (:66-80)
-		uint32_t id = (s.board[slot >> 2] >> (8 * (slot & 3))) & 0xFFu;
+	// 12 board slots (:66-80) + my 3 reserved cards (:89-91): one loop body, kept rolled on purpose -- the step
+	// kernels are instruction-cache bound, not ALU bound
+	uint32_t afford = 0, present = 0;
+#pragma unroll 3
+	for (uint32_t slot = 0; slot < 15; slot++) {
+		uint32_t word = slot < 4 ? s.board[0] : (slot < 8 ? s.board[1] : (slot < 12 ? s.board[2] : s.res[0]));
+		uint32_t id = (word >> (8 * (slot & 3))) & 0xFFu;
 		uint32_t info = T->card_info[spl_min(id, 90u)];
 		bool here = id != SPL_EMPTY;
 		present |= here ? (1u << slot) : 0u;
-		buy |= (here && spl_shortfall(info, wealth) <= gold) ? (1u << slot) : 0u;
+		afford |= (here && spl_shortfall(info, wealth) <= gold) ? (1u << slot) : 0u;
 	}
-	uint32_t buyres = 0;
-#pragma unroll
-	for (int i = 0; i < 3; i++) {                        // (:89-91)
-		uint32_t id = (s.res[0] >> (8 * i)) & 0xFFu;
-		uint32_t info = T->card_info[spl_min(id, 90u)];
-		buyres |= (id != SPL_EMPTY && spl_shortfall(info, wealth) <= gold) ? (1u << i) : 0u;
-	}
+	const uint32_t buy = afford & 0xFFFu, buyres = afford >> 12;
+	present &= 0xFFFu;
 	bool can_reserve = s.nres[0] < 3;                    // (:74, :83)
 	uint32_t blind = spl_compress_flags4(spl_ge_flags4(s.deckn, 1)) & 7u;
 	m_lo |= buy << 15;                                    // bits 15..26
@@ -416,8 +414,11 @@ struct SplStepResult {
 // SplendorEnv.step (envs/splendor_env.py:51-90) + apply_action (engine/rules.py:196-287) in place.
 // `deck` = this env's deck-order row (top of tier t = deck[off_t + deckn_t - 1]).
 // ------------------------------------------------------------------------------------------------
-SPL_HD void spl_env_step(SplState& s, int32_t action, const uint8_t* deck, const SplTables* T, const uint64_t* ret_table,
-                         SplStepResult& out) {
+// KNOWN_MASK: the caller already holds legal_moves(state) as a bit set (`cur_mask`) -- the reference computes
+// exactly that at the top of step() (:55) -- otherwise legality is evaluated for the one action only.
+template <bool KNOWN_MASK>
+SPL_HD void spl_env_step_t(SplState& s, int32_t action, const uint8_t* deck, const SplTables* T, const uint64_t* ret_table,
+                           SplStepResult& out, uint64_t cur_mask) {
 	out.reward = 0.0f;
 	out.terminated = 0;
 	out.info = 0;
@@ -430,8 +431,13 @@ SPL_HD void spl_env_step(SplState& s, int32_t action, const uint8_t* deck, const
 	const uint32_t avail = spl_colours_ge(s.bank, 1);
 	// any legal move? a non-empty bank always allows a take-3 (:45-58), so the full mask is only
 	// needed when all five colours are exhausted
-	bool any = avail != 0;
-	if (!any) any = spl_legal_mask(s, T) != 0;
+	bool any;
+	if (KNOWN_MASK) {
+		any = cur_mask != 0;
+	} else {
+		any = avail != 0;
+		if (!any) any = spl_legal_mask(s, T) != 0;
+	}
 	if (!any) {  // no-legal-move draw (:55-61): game_over, winner None, to_play = 0; counters untouched
 		s.flags = (s.flags | SPL_FLAG_GAME_OVER) & ~(SPL_FLAG_WINNER_MASK | SPL_FLAG_TO_PLAY);
 		if (tp) spl_swap_players(s);
@@ -444,7 +450,8 @@ SPL_HD void spl_env_step(SplState& s, int32_t action, const uint8_t* deck, const
 		out.info = SPL_INFO_ERROR;
 		return;
 	}
-	if (!spl_action_legal(s, a, avail, T)) {  // (:64-66)
+	const bool legal = KNOWN_MASK ? (((cur_mask >> a) & 1ull) != 0) : spl_action_legal(s, a, avail, T);
+	if (!legal) {  // (:64-66)
 		out.reward = -0.01f;
 		out.info = SPL_INFO_ILLEGAL;
 		return;
@@ -589,6 +596,11 @@ SPL_HD void spl_env_step(SplState& s, int32_t action, const uint8_t* deck, const
 	if (err) out.info |= SPL_INFO_ERROR;
 }
 
+SPL_HD void spl_env_step(SplState& s, int32_t action, const uint8_t* deck, const SplTables* T, const uint64_t* ret_table,
+                         SplStepResult& out) {
+	spl_env_step_t<false>(s, action, deck, T, ret_table, out, 0ull);
+}
+
 // ------------------------------------------------------------------------------------------------
 // encode_observation (engine/encode.py:124-187) as 75 little-endian words of one byte per entry
 // (entries 297..299 are zero padding).  `w` is the PACKED row of the same state: words 0..7 are
@@ -623,62 +635,64 @@ SPL_HD SplFeat spl_card_feat(const SplTables* T, uint32_t id) {
 #endif
 }
 
-template <class Emit>
-SPL_HD void spl_encode_observation(const uint32_t* w, const SplState& s, const SplTables* T, Emit&& emit) {
+// Sink interface: first(v) = word 0, put(k, v) for 1 <= k <= 73 (k may be a run-time value), last(v) = word 74.
+template <class Sink>
+SPL_HD void spl_encode_observation(const uint32_t* w, const SplState& s, const SplTables* T, Sink& sink) {
 	// [0:32) bank, me, opponent
+	sink.first(w[0]);
 #pragma unroll
-	for (int k = 0; k < 8; k++) emit(k, w[k]);
+	for (int k = 1; k < 8; k++) sink.put(k, w[k]);
 	// [32:188) board: 12 cards x 13 entries; four cards = 52 bytes = 13 words (records at byte 0,13,26,39)
-#pragma unroll
+#pragma unroll 1
 	for (int t = 0; t < 3; t++) {
-		uint32_t ids = s.board[t];
+		uint32_t ids = t == 0 ? s.board[0] : (t == 1 ? s.board[1] : s.board[2]);
 		SplFeat A = spl_card_feat(T, ids & 0xFF), B = spl_card_feat(T, (ids >> 8) & 0xFF);
 		SplFeat C = spl_card_feat(T, (ids >> 16) & 0xFF), D = spl_card_feat(T, ids >> 24);
 		int k = 8 + 13 * t;
-		emit(k + 0, A.x);
-		emit(k + 1, A.y);
-		emit(k + 2, A.z);
-		emit(k + 3, spl_bp(A.w, B.x, 0x6540));                          // A12 B0 B1 B2
-		emit(k + 4, spl_bp(B.x, B.y, 0x6543));                          // B3..B6
-		emit(k + 5, spl_bp(B.y, B.z, 0x6543));                          // B7..B10
-		emit(k + 6, spl_bp(spl_bp(B.z, B.w, 0x0043), C.x, 0x5410));     // B11 B12 C0 C1
-		emit(k + 7, spl_bp(C.x, C.y, 0x5432));                          // C2..C5
-		emit(k + 8, spl_bp(C.y, C.z, 0x5432));                          // C6..C9
-		emit(k + 9, spl_bp(spl_bp(C.z, C.w, 0x0432), D.x, 0x4210));     // C10 C11 C12 D0
-		emit(k + 10, spl_bp(D.x, D.y, 0x4321));                         // D1..D4
-		emit(k + 11, spl_bp(D.y, D.z, 0x4321));                         // D5..D8
-		emit(k + 12, spl_bp(D.z, D.w, 0x4321));                         // D9..D12
+		sink.put(k + 0, A.x);
+		sink.put(k + 1, A.y);
+		sink.put(k + 2, A.z);
+		sink.put(k + 3, spl_bp(A.w, B.x, 0x6540));                          // A12 B0 B1 B2
+		sink.put(k + 4, spl_bp(B.x, B.y, 0x6543));                          // B3..B6
+		sink.put(k + 5, spl_bp(B.y, B.z, 0x6543));                          // B7..B10
+		sink.put(k + 6, spl_bp(spl_bp(B.z, B.w, 0x0043), C.x, 0x5410));     // B11 B12 C0 C1
+		sink.put(k + 7, spl_bp(C.x, C.y, 0x5432));                          // C2..C5
+		sink.put(k + 8, spl_bp(C.y, C.z, 0x5432));                          // C6..C9
+		sink.put(k + 9, spl_bp(spl_bp(C.z, C.w, 0x0432), D.x, 0x4210));     // C10 C11 C12 D0
+		sink.put(k + 10, spl_bp(D.x, D.y, 0x4321));                         // D1..D4
+		sink.put(k + 11, spl_bp(D.y, D.z, 0x4321));                         // D5..D8
+		sink.put(k + 12, spl_bp(D.z, D.w, 0x4321));                         // D9..D12
 	}
 	// [188:272) reserved: my three (always revealed=1), then the opponent's (a hidden one is 14 zeros,
 	// engine/encode.py:158-168).  Six 14-entry records = three aligned pairs of 7 words.
-	uint32_t mine = s.res[0];
-	uint32_t rv = s.rev[1];
-	uint32_t theirs = s.res[1] | ((rv & 1u) ? 0u : 0xFFu) | ((rv & 2u) ? 0u : 0xFF00u) | ((rv & 4u) ? 0u : 0xFF0000u);
-	uint32_t rid[6] = {mine & 0xFF, (mine >> 8) & 0xFF, (mine >> 16) & 0xFF, theirs & 0xFF, (theirs >> 8) & 0xFF, (theirs >> 16) & 0xFF};
-#pragma unroll
+	const uint32_t rv = s.rev[1];
+	const uint32_t theirs = s.res[1] | ((rv & 1u) ? 0u : 0xFFu) | ((rv & 2u) ? 0u : 0xFF00u) | ((rv & 4u) ? 0u : 0xFF0000u);
+	const uint64_t six = (uint64_t)s.res[0] | ((uint64_t)theirs << 24);
+#pragma unroll 1
 	for (int pr = 0; pr < 3; pr++) {
-		SplFeat X = spl_card_feat(T, rid[2 * pr]), Y = spl_card_feat(T, rid[2 * pr + 1]);
+		uint32_t two = (uint32_t)(six >> (16 * pr));
+		SplFeat X = spl_card_feat(T, two & 0xFF), Y = spl_card_feat(T, (two >> 8) & 0xFF);
 		int k = 47 + 7 * pr;
-		emit(k + 0, X.x);
-		emit(k + 1, X.y);
-		emit(k + 2, X.z);
-		emit(k + 3, spl_bp(X.w, Y.x, 0x5410));  // X12 X13 Y0 Y1
-		emit(k + 4, spl_bp(Y.x, Y.y, 0x5432));  // Y2..Y5
-		emit(k + 5, spl_bp(Y.y, Y.z, 0x5432));  // Y6..Y9
-		emit(k + 6, spl_bp(Y.z, Y.w, 0x5432));  // Y10..Y13
+		sink.put(k + 0, X.x);
+		sink.put(k + 1, X.y);
+		sink.put(k + 2, X.z);
+		sink.put(k + 3, spl_bp(X.w, Y.x, 0x5410));  // X12 X13 Y0 Y1
+		sink.put(k + 4, spl_bp(Y.x, Y.y, 0x5432));  // Y2..Y5
+		sink.put(k + 5, spl_bp(Y.y, Y.z, 0x5432));  // Y6..Y9
+		sink.put(k + 6, spl_bp(Y.z, Y.w, 0x5432));  // Y10..Y13
 	}
 	// [272:290) nobles 3 x (present, req5); [290:293) deck sizes; turn_count, to_play, move_count, terminal
 	{
 		const uint32_t* X = T->noble_feat[spl_min(s.nobles & 0xFF, 10u)];
 		const uint32_t* Y = T->noble_feat[spl_min((s.nobles >> 8) & 0xFF, 10u)];
 		const uint32_t* Z = T->noble_feat[spl_min((s.nobles >> 16) & 0xFF, 10u)];
-		emit(68, X[0]);
-		emit(69, spl_bp(X[1], Y[0], 0x5410));
-		emit(70, spl_bp(Y[0], Y[1], 0x5432));
-		emit(71, Z[0]);
-		emit(72, spl_bp(Z[1], s.deckn, 0x5410));
-		emit(73, ((s.deckn >> 16) & 0xFFu) | (s.turn << 8) | ((s.flags & SPL_FLAG_TO_PLAY) << 16) | (s.move << 24));
-		emit(74, spl_is_terminal(s) ? 1u : 0u);
+		sink.put(68, X[0]);
+		sink.put(69, spl_bp(X[1], Y[0], 0x5410));
+		sink.put(70, spl_bp(Y[0], Y[1], 0x5432));
+		sink.put(71, Z[0]);
+		sink.put(72, spl_bp(Z[1], s.deckn, 0x5410));
+		sink.put(73, ((s.deckn >> 16) & 0xFFu) | (s.turn << 8) | ((s.flags & SPL_FLAG_TO_PLAY) << 16) | (s.move << 24));
+		sink.last(spl_is_terminal(s) ? 1u : 0u);
 	}
 }
 

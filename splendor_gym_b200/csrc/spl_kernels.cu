@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "spl_core.cuh"
 #include "spl_tables_host.h"
@@ -29,7 +30,7 @@ __device__ uint64_t g_ret_table[SPL_RET_TABLE_LEN];
 // Philox4x32-10 (Salmon et al., SC'11) -- counter-based stream for action sampling and native shuffles
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 spl_philox(uint4 c, uint32_t k0, uint32_t k1) {
-#pragma unroll
+#pragma unroll 2
 	for (int r = 0; r < 10; r++) {
 		uint32_t h0 = __umulhi(0xD2511F53u, c.x), l0 = 0xD2511F53u * c.x;
 		uint32_t h1 = __umulhi(0xCD9E8D57u, c.z), l1 = 0xCD9E8D57u * c.z;
@@ -76,7 +77,7 @@ __device__ __forceinline__ int32_t spl_sample_action(uint64_t m, uint64_t key, u
 // [32 x 45] int8 action-mask tile from one 45-bit set per lane.  `rows` = valid envs in the tile.
 __device__ __forceinline__ void spl_store_mask_tile(int8_t* gtile, uint64_t m, int lane, int rows) {
 	const int tile_bytes = rows * SPL_NUM_ACTIONS;
-#pragma unroll
+#pragma unroll 1
 	for (int it = 0; it < 3; it++) {
 		int q = lane + 32 * it;  // int4 index, 90 per full tile
 		int byte0 = 16 * q;
@@ -109,22 +110,22 @@ struct SplObsStager {
 	    : dst(tile + ((SPL_OBS_DIM * lane) >> 2)), shift8(8u * (lane & 3)), prev(0) {
 		next_r0 = __shfl_down_sync(SPL_FULL, w0, 1);
 	}
-	__device__ __forceinline__ void operator()(int k, uint32_t v) {
-		if (k == 74) v |= next_r0 << 8;
-		if (k == 0) {
-			if (shift8 == 0) dst[0] = v;
-		} else {
-			dst[k] = __funnelshift_l(prev, v, shift8);
-		}
+	__device__ __forceinline__ void first(uint32_t v) {
+		if (shift8 == 0) dst[0] = v;
 		prev = v;
 	}
+	__device__ __forceinline__ void put(int k, uint32_t v) {
+		dst[k] = __funnelshift_l(prev, v, shift8);
+		prev = v;
+	}
+	__device__ __forceinline__ void last(uint32_t v) { put(74, v | (next_r0 << 8)); }
 };
 
 // stream a staged tile to global memory as int32 (rows == 32: 2376 aligned int4; otherwise per entry)
 __device__ __forceinline__ void spl_store_obs_tile(int32_t* gtile, const uint32_t* tile, int lane, int rows, bool vec) {
 	if (rows == 32 && vec) {
 		int4* g4 = reinterpret_cast<int4*>(gtile);
-#pragma unroll 6
+#pragma unroll 2
 		for (int q = lane; q < SPL_TILE_WORDS; q += 32) {
 			uint32_t v = tile[q];
 			int4 o = make_int4((int)(v & 0xFFu), (int)((v >> 8) & 0xFFu), (int)((v >> 16) & 0xFFu), (int)(v >> 24));
@@ -161,7 +162,7 @@ __device__ __forceinline__ void spl_coop_deal(uint64_t seed, uint64_t genv, uint
 		const uint32_t e0 = lane, e1 = 32 + lane;
 		const uint32_t k0 = keys[e0], k1 = keys[e1 < 40 ? e1 : 0];
 		uint32_t r0 = 0, r1 = 0;
-#pragma unroll 8
+#pragma unroll 4
 		for (uint32_t i = 0; i < 40; i++) {
 			uint32_t ki = keys[i];
 			r0 += (ki < k0) || (ki == k0 && i < e0);
@@ -174,17 +175,17 @@ __device__ __forceinline__ void spl_coop_deal(uint64_t seed, uint64_t genv, uint
 		const uint32_t e2 = 40 + lane, e3 = 70 + lane, e4 = 90 + lane;
 		const uint32_t k2 = keys[lane < 30 ? e2 : 40], k3 = keys[lane < 20 ? e3 : 70], k4 = keys[lane < 10 ? e4 : 90];
 		uint32_t r2 = 0, r3 = 0, r4 = 0;
-#pragma unroll 6
+#pragma unroll 2
 		for (uint32_t i = 40; i < 70; i++) {
 			uint32_t ki = keys[i];
 			r2 += (ki < k2) || (ki == k2 && i < e2);
 		}
-#pragma unroll 5
+#pragma unroll 2
 		for (uint32_t i = 70; i < 90; i++) {
 			uint32_t ki = keys[i];
 			r3 += (ki < k3) || (ki == k3 && i < e3);
 		}
-#pragma unroll
+#pragma unroll 2
 		for (uint32_t i = 90; i < 100; i++) {
 			uint32_t ki = keys[i];
 			r4 += (ki < k4) || (ki == k4 && i < e4);
@@ -240,6 +241,7 @@ struct StepParams {
 	int reset_mode;
 	int vec_ok;  // obs / mask bases are 16-byte aligned
 	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
+	int sync;    // rollout kernel: CTA barrier per lock-step (keeps the warps of a CTA in the same code region)
 };
 
 struct SplTile {
@@ -251,11 +253,12 @@ struct SplTile {
 };
 
 // one SplendorEnv.step for the lane's env + episode statistics + same-step auto-reset
+template <bool KNOWN_MASK>
 __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile& tl, SplState& s, bool act, int32_t action, int64_t env,
-                                              SplStepResult& r) {
+                                              SplStepResult& r, uint64_t cur_mask = 0) {
 	const int lane = tl.lane;
 	r.reward = 0.0f, r.terminated = 0, r.info = 0;
-	if (act) spl_env_step(s, action, p.decks + env * SPL_DECK_STRIDE, tl.T, g_ret_table, r);
+	if (act) spl_env_step_t<KNOWN_MASK>(s, action, p.decks + env * SPL_DECK_STRIDE, tl.T, g_ret_table, r, cur_mask);
 	const bool finished = r.terminated && !(r.info & SPL_INFO_ERROR);
 	const bool do_reset = act && r.terminated && p.reset_mode != SPL_RESET_NONE;
 	if (do_reset) r.info |= SPL_INFO_RESET;
@@ -305,13 +308,11 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 }
 
 // outputs of the lane's (possibly new) state: legal mask tile, sampled next action, observation tile
+// `m` = legal_moves of that state as a bit set (all-zero once terminal, envs/splendor_env.py:81)
 __device__ __forceinline__ int32_t spl_tile_emit(const StepParams& p, const SplTile& tl, const SplState& s, const uint32_t* w, int64_t env,
-                                                 bool valid, int32_t* obs, int8_t* mask, int32_t* next_action, uint64_t t) {
+                                                 bool valid, int32_t* obs, int8_t* mask, int32_t* next_action, uint64_t t, uint64_t m) {
 	const int lane = tl.lane;
-	// legal_moves of the resulting state (all-zero once terminal, envs/splendor_env.py:81)
-	uint64_t m = 0;
 	int32_t sampled = 0;
-	if (mask != nullptr || next_action != nullptr) m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, tl.T);
 	if (mask != nullptr) {
 		if (p.vec_ok) spl_store_mask_tile(mask + tl.ti * 32 * SPL_NUM_ACTIONS, m, lane, tl.rows);
 		else if (valid)
@@ -359,10 +360,10 @@ __device__ __forceinline__ const SplTables* spl_stage_tables(SplTables* T) {
 }
 
 // one lock-step (DO_STEP) or just encode_observation + legal_moves of the current states
-template <bool DO_STEP>
-__global__ void __launch_bounds__(SPL_WARPS_PER_CTA * 32) spl_step_kernel(const StepParams p) {
+template <bool DO_STEP, int WPC>
+__global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) {
 	__shared__ SplTables Ts;
-	__shared__ __align__(16) uint32_t tiles[SPL_WARPS_PER_CTA][SPL_TILE_WORDS];
+	__shared__ __align__(16) uint32_t tiles[WPC][SPL_TILE_WORDS];
 	SplTile tl;
 	tl.T = spl_stage_tables(&Ts);
 	tl.lane = threadIdx.x & 31;
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(SPL_WARPS_PER_CTA * 32) spl_step_kernel(const 
 	const int64_t ntiles = (p.n + 31) >> 5;
 	const uint64_t t = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
 
-	for (tl.ti = (int64_t)blockIdx.x * SPL_WARPS_PER_CTA + warp; tl.ti < ntiles; tl.ti += (int64_t)gridDim.x * SPL_WARPS_PER_CTA) {
+	for (tl.ti = (int64_t)blockIdx.x * WPC + warp; tl.ti < ntiles; tl.ti += (int64_t)gridDim.x * WPC) {
 		const int64_t env = tl.ti * 32 + tl.lane;
 		const bool valid = env < p.n;
 		tl.rows = (int)min((int64_t)32, p.n - tl.ti * 32);
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(SPL_WARPS_PER_CTA * 32) spl_step_kernel(const 
 		if (DO_STEP) {
 			const bool act = valid && (p.active == nullptr || p.active[env] != 0);
 			SplStepResult r;
-			spl_tile_step(p, tl, s, act, act ? p.actions[env] : 0, env, r);
+			spl_tile_step<false>(p, tl, s, act, act ? p.actions[env] : 0, env, r);
 			if (act) {
 				spl_pack(s, w);
 				spl_store_state(p, env, w);
@@ -393,16 +394,19 @@ __global__ void __launch_bounds__(SPL_WARPS_PER_CTA * 32) spl_step_kernel(const 
 				p.info[env] = (uint8_t)r.info;
 			}
 		}
-		spl_tile_emit(p, tl, s, w, env, valid, p.obs, p.mask, p.next_action, t);
+		uint64_t m = 0;
+		if (p.mask != nullptr || p.next_action != nullptr) m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, tl.T);
+		spl_tile_emit(p, tl, s, w, env, valid, p.obs, p.mask, p.next_action, t, m);
 	}
 }
 
 // `steps` lock-steps of uniform-random-legal play with same-step auto-reset in ONE launch: every warp keeps its
 // 32 games in registers and streams each step's observation / mask / reward / terminated / action into
 // [steps][n][...] rollout buffers.  Bit-identical to `steps` calls of spl_step chained through next_action.
-__global__ void __launch_bounds__(SPL_WARPS_PER_CTA * 32) spl_rollout_kernel(const StepParams p) {
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32) spl_rollout_kernel(const StepParams p) {
 	__shared__ SplTables Ts;
-	__shared__ __align__(16) uint32_t tiles[SPL_WARPS_PER_CTA][SPL_TILE_WORDS];
+	__shared__ __align__(16) uint32_t tiles[WPC][SPL_TILE_WORDS];
 	SplTile tl;
 	tl.T = spl_stage_tables(&Ts);
 	tl.lane = threadIdx.x & 31;
@@ -411,27 +415,38 @@ __global__ void __launch_bounds__(SPL_WARPS_PER_CTA * 32) spl_rollout_kernel(con
 	const int64_t ntiles = (p.n + 31) >> 5;
 	const uint64_t t0 = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
 
-	for (tl.ti = (int64_t)blockIdx.x * SPL_WARPS_PER_CTA + warp; tl.ti < ntiles; tl.ti += (int64_t)gridDim.x * SPL_WARPS_PER_CTA) {
+	// CTA-uniform trip count (tile groups of SPL_WARPS_PER_CTA) so that the optional per-step barrier is safe
+	for (int64_t tg = blockIdx.x; tg * WPC < ntiles; tg += gridDim.x) {
+		tl.ti = tg * WPC + warp;
 		const int64_t env = tl.ti * 32 + tl.lane;
 		const bool valid = env < p.n;
-		tl.rows = (int)min((int64_t)32, p.n - tl.ti * 32);
+		tl.rows = (int)max((int64_t)0, min((int64_t)32, p.n - tl.ti * 32));
 		uint32_t w[16];
 		spl_load_state(p, env, valid, w);
 		SplState s;
 		spl_unpack(w, s);
 		int32_t action = valid ? p.actions[env] : 0;
-		for (int st = 0; st < p.steps; st++) {
+		// rotated loop: [legal mask of the current state] -> [emit the outputs of the previous step] -> [step].
+		// The mask is needed twice -- as the action mask returned by step t-1 and as the legality check of
+		// step t (envs/splendor_env.py:55,64,81) -- and is computed once; one code copy keeps the hot loop small.
+		for (int st = 0; st <= p.steps; st++) {
+			if (p.sync) __syncthreads();
+			const uint64_t m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, tl.T);
+			if (st > 0) {
+				const int64_t o = (int64_t)(st - 1) * p.n;
+				action = spl_tile_emit(p, tl, s, w, env, valid, p.obs ? p.obs + o * SPL_OBS_DIM : nullptr,
+				                       p.mask ? p.mask + o * SPL_NUM_ACTIONS : nullptr, p.next_action + o + p.n, t0 + (uint64_t)(st - 1), m);
+			}
+			if (st == p.steps) break;
 			const int64_t o = (int64_t)st * p.n;
 			SplStepResult r;
-			spl_tile_step(p, tl, s, valid, action, env, r);
+			spl_tile_step<true>(p, tl, s, valid, action, env, r, m);
 			spl_pack(s, w);
 			if (valid) {
 				p.reward[o + env] = r.reward;
 				p.terminated[o + env] = (uint8_t)r.terminated;
 				if (p.info != nullptr) p.info[o + env] = (uint8_t)r.info;
 			}
-			action = spl_tile_emit(p, tl, s, w, env, valid, p.obs ? p.obs + o * SPL_OBS_DIM : nullptr,
-			                       p.mask ? p.mask + o * SPL_NUM_ACTIONS : nullptr, p.next_action + o + p.n, t0 + (uint64_t)st);
 		}
 		if (valid) spl_store_state(p, env, w);
 	}
@@ -757,7 +772,7 @@ __global__ void spl_dual_combine_kernel(const float* r1, const uint8_t* t1, cons
 // ------------------------------------------------------------------------------------------------
 static int g_inited_device = -1;
 static int g_num_sms = 0;
-static int g_step_ctas_per_sm = 0, g_obs_ctas_per_sm = 0, g_roll_ctas_per_sm = 0;
+static int g_occ[3][2];  // [kernel: step, observe, rollout][wpc 1 / 4] resident CTAs per SM
 static uint64_t g_host_ret[SPL_RET_TABLE_LEN];
 static bool g_host_ret_built = false;
 static int64_t g_launches = 0;
@@ -840,15 +855,15 @@ int spl_init(void) {
 	SPL_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
 	SPL_CUDA(cudaFuncSetAttribute(spl_reset_kernel<SPL_SHUFFLE_MT19937>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPL_MT_SMEM));
 	SPL_CUDA(cudaFuncSetAttribute(spl_reset_kernel<SPL_SHUFFLE_PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPL_PHILOX_SMEM));
-	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_step_ctas_per_sm, spl_step_kernel<true>, SPL_WARPS_PER_CTA * 32, 0));
-	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_obs_ctas_per_sm, spl_step_kernel<false>, SPL_WARPS_PER_CTA * 32, 0));
-	SPL_CUDA(cudaFuncSetAttribute(spl_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_roll_ctas_per_sm, spl_rollout_kernel, SPL_WARPS_PER_CTA * 32, 0));
-	if (g_roll_ctas_per_sm < 1) g_roll_ctas_per_sm = 1;
-	if (g_step_ctas_per_sm < 1) g_step_ctas_per_sm = 1;
-	if (g_obs_ctas_per_sm < 1) g_obs_ctas_per_sm = 1;
+#define SPL_SETUP(K, kid, slot, threads)                                                                     \
+	SPL_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[kid][slot], K, threads, 0));                       \
+	if (g_occ[kid][slot] < 1) g_occ[kid][slot] = 1;
+	SPL_SETUP((spl_step_kernel<true, 4>), 0, 1, 128)
+	SPL_SETUP((spl_step_kernel<false, 4>), 1, 1, 128)
+	SPL_SETUP((spl_rollout_kernel<1>), 2, 0, 32)
+	SPL_SETUP((spl_rollout_kernel<4>), 2, 1, 128)
+#undef SPL_SETUP
 	SPL_CUDA(cudaDeviceSynchronize());
 	g_inited_device = dev;
 	return 0;
@@ -910,22 +925,41 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	if (io && io->autoreset) p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED : SPL_RESET_WORKLIST;
 	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;
 	p.steps = 1;
+	p.sync = 0;
 }
 
-static int step_grid(int64_t n, int ctas_per_sm) {
-	int64_t ctas = ((n + 31) / 32 + SPL_WARPS_PER_CTA - 1) / SPL_WARPS_PER_CTA;
-	int64_t cap = (int64_t)g_num_sms * ctas_per_sm;
-	return (int)(ctas < cap ? ctas : cap);
+// Launch shape.  Few tiles (every warp resident at once, e.g. 65,536 envs = 2,048 tiles): 1-warp CTAs spread the
+// tiles evenly over the 148 SMs and no barrier is used (the run is latency-bound).  Many tiles: 4-warp CTAs,
+// persistent over tile groups; the rollout kernel then adds one CTA barrier per lock-step, which keeps the
+// warps of a CTA in the same code region (the kernels are instruction-fetch sensitive: ~37 KB of hot SASS).
+struct LaunchShape {
+	int wpc, grid, sync;
+};
+
+static LaunchShape launch_shape(int64_t n, int kernel) {
+	const int64_t ntiles = (n + 31) / 32;
+	LaunchShape L;
+	const char* e = getenv("SPL_WPC");
+	int64_t resident4 = (int64_t)g_num_sms * g_occ[kernel][1] * 4;
+	// single-step kernels always use 4-warp CTAs (the 2 KB table staging is paid per CTA per launch)
+	L.wpc = kernel != 2 ? 4 : (e ? atoi(e) : (ntiles <= resident4 ? 1 : 4));
+	if (L.wpc != 1) L.wpc = 4;
+	int64_t ctas = (ntiles + L.wpc - 1) / L.wpc;
+	int64_t cap = (int64_t)g_num_sms * g_occ[kernel][L.wpc == 1 ? 0 : 1];
+	L.grid = (int)(ctas < cap ? ctas : cap);
+	const char* sy = getenv("SPL_ROLLOUT_SYNC");
+	L.sync = sy ? atoi(sy) : (L.wpc == 4 && ctas > cap);
+	return L;
 }
 
 static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, int32_t* obs, int8_t* mask, cudaStream_t st) {
 	StepParams p;
 	fill_step_params(p, e, io, obs, mask);
-	int grid = step_grid(e->n, do_step ? g_step_ctas_per_sm : g_obs_ctas_per_sm);
+	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
-	if (do_step) spl_step_kernel<true><<<grid, SPL_WARPS_PER_CTA * 32, 0, st>>>(p);
-	else spl_step_kernel<false><<<grid, SPL_WARPS_PER_CTA * 32, 0, st>>>(p);
+	if (do_step) spl_step_kernel<true, 4><<<L.grid, 128, 0, st>>>(p);
+	else spl_step_kernel<false, 4><<<L.grid, 128, 0, st>>>(p);
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
 	g_launches++;
 	return (int)cudaGetLastError();
@@ -960,11 +994,13 @@ int spl_rollout_random(const spl_envs_t* envs, const spl_step_io_t* io, int32_t 
 	p.steps = steps;
 	// every step's tile must stay 16-byte aligned: n*297*4 and n*45 are multiples of 16 iff n % 16 == 0
 	if (envs->n % 16 != 0) p.vec_ok = 0;
-	int grid = step_grid(envs->n, g_roll_ctas_per_sm);
+	LaunchShape L = launch_shape(envs->n, 2);
+	p.sync = L.sync;
 	cudaStream_t st = (cudaStream_t)stream;
 	const bool timed = g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
-	spl_rollout_kernel<<<grid, SPL_WARPS_PER_CTA * 32, 0, st>>>(p);
+	if (L.wpc == 1) spl_rollout_kernel<1><<<L.grid, 32, 0, st>>>(p);
+	else spl_rollout_kernel<4><<<L.grid, 128, 0, st>>>(p);
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
 	g_launches++;
 	return (int)cudaGetLastError();

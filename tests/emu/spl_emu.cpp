@@ -6,6 +6,13 @@
 
 #include "../../splendor_gym_b200/csrc/spl_tables_host.h"
 
+struct ArraySink {
+	uint32_t* R;
+	void first(uint32_t v) { R[0] = v; }
+	void put(int k, uint32_t v) { R[k] = v; }
+	void last(uint32_t v) { R[74] = v; }
+};
+
 static SplTables g_T;
 static uint64_t g_ret[SPL_RET_TABLE_LEN];
 static bool g_init = false;
@@ -47,7 +54,8 @@ void emu_observe(const int32_t* row, int32_t* obs, int8_t* mask) {
 	uint64_t m = spl_is_terminal(s) ? 0 : spl_legal_mask(s, &g_T);
 	for (int i = 0; i < SPL_NUM_ACTIONS; i++) mask[i] = (int8_t)((m >> i) & 1);
 	uint32_t R[75];
-	spl_encode_observation(w, s, &g_T, [&](int k, uint32_t v) { R[k] = v; });
+	ArraySink sink{R};
+	spl_encode_observation(w, s, &g_T, sink);
 	for (int i = 0; i < SPL_OBS_DIM; i++) obs[i] = (int32_t)((R[i >> 2] >> (8 * (i & 3))) & 0xFF);
 }
 
@@ -66,7 +74,8 @@ void emu_env_step(const int32_t* row, int32_t action, int32_t* row_out, int32_t*
 	uint64_t m = spl_is_terminal(s) ? 0 : spl_legal_mask(s, &g_T);
 	for (int i = 0; i < SPL_NUM_ACTIONS; i++) mask[i] = (int8_t)((m >> i) & 1);
 	uint32_t R[75];
-	spl_encode_observation(w, s, &g_T, [&](int k, uint32_t v) { R[k] = v; });
+	ArraySink sink{R};
+	spl_encode_observation(w, s, &g_T, sink);
 	for (int i = 0; i < SPL_OBS_DIM; i++) obs[i] = (int32_t)((R[i >> 2] >> (8 * (i & 3))) & 0xFF);
 	*reward = r.reward;
 	*terminated = (uint8_t)r.terminated;
