@@ -153,10 +153,12 @@ int spl_random_action(const int8_t *mask, int64_t n, uint64_t env_offset, uint64
 int spl_export_state(const spl_envs_t *envs, int32_t *rows, void *stream);
 int spl_import_state(const spl_envs_t *envs, const int32_t *rows, const uint8_t *which, void *stream);
 
-/* DualStepNativeWrapper.dual_step reward bookkeeping (wrappers/dual_step_native.py:132-167,195-201):
- * combines phase-1 (agent) and phase-2 (opponent) step results into agent_reward / opp_reward / done. */
+/* Self-play turn bookkeeping: combines phase-1 (agent = player 0) and phase-2 (opponent) step results into
+ * agent_reward / opp_reward / done.  mode 0 = DualStepNativeWrapper.dual_step (wrappers/dual_step_native.py:132-167,
+ * 195-201; also DualStepSelfPlayWrapper, wrappers/dual_step_selfplay.py:138-152): agent reward = final_rewards[0];
+ * mode 1 = SelfPlayWrapper.step (wrappers/selfplay.py:42-63): agent reward = -opponent reward. */
 int spl_dual_combine(const float *r1, const uint8_t *term1, const uint8_t *info1, const float *r2, const uint8_t *term2,
-                     const uint8_t *info2, int64_t n, float *agent_reward, float *opp_reward, uint8_t *done,
+                     const uint8_t *info2, int64_t n, float *agent_reward, float *opp_reward, uint8_t *done, int mode,
                      void *stream);
 
 const char *spl_error_string(int code);

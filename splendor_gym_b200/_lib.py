@@ -96,7 +96,7 @@ def load():
     L.spl_import_state.restype = C.c_int
     L.spl_import_state.argtypes = [C.POINTER(SplEnvs), vp, vp, vp]
     L.spl_dual_combine.restype = C.c_int
-    L.spl_dual_combine.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]
+    L.spl_dual_combine.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, C.c_int, vp]
     L.spl_error_string.restype = C.c_char_p
     L.spl_error_string.argtypes = [C.c_int]
     L.spl_version.restype = C.c_int

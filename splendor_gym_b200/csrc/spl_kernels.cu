@@ -748,8 +748,10 @@ __device__ __forceinline__ float spl_final_reward(uint32_t info, uint32_t player
 }
 
 // wrappers/dual_step_native.py:132-167: phase 1 = agent (player 0), phase 2 = opponent (player 1)
+// mode 0: DualStepNativeWrapper / DualStepSelfPlayWrapper (agent reward = final_rewards[0]);
+// mode 1: SelfPlayWrapper (agent reward = -opponent reward when the opponent's move ends the game, selfplay.py:55-57)
 __global__ void spl_dual_combine_kernel(const float* r1, const uint8_t* t1, const uint8_t* i1, const float* r2, const uint8_t* t2,
-                                        const uint8_t* i2, int64_t n, float* agent_reward, float* opp_reward, uint8_t* done) {
+                                        const uint8_t* i2, int64_t n, float* agent_reward, float* opp_reward, uint8_t* done, int mode) {
 	int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (e >= n) return;
 	if (t1[e]) {  // game ended on the agent's move (:132-145)
@@ -761,7 +763,7 @@ __global__ void spl_dual_combine_kernel(const float* r1, const uint8_t* t1, cons
 		opp_reward[e] = 0.0f;
 		done[e] = 0;
 	} else {  // (:157-167)
-		agent_reward[e] = t2[e] ? spl_final_reward(i2[e], 0) : 0.0f;
+		agent_reward[e] = t2[e] ? (mode == 1 ? -r2[e] : spl_final_reward(i2[e], 0)) : 0.0f;
 		opp_reward[e] = r2[e];
 		done[e] = t2[e];
 	}
@@ -1043,10 +1045,10 @@ int spl_import_state(const spl_envs_t* envs, const int32_t* rows, const uint8_t*
 }
 
 int spl_dual_combine(const float* r1, const uint8_t* term1, const uint8_t* info1, const float* r2, const uint8_t* term2,
-                     const uint8_t* info2, int64_t n, float* agent_reward, float* opp_reward, uint8_t* done, void* stream) {
+                     const uint8_t* info2, int64_t n, float* agent_reward, float* opp_reward, uint8_t* done, int mode, void* stream) {
 	if (!r1 || !term1 || !info1 || !r2 || !term2 || !info2 || !agent_reward || !opp_reward || !done || n <= 0) return SPL_E_BADARG;
 	spl_dual_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r1, term1, info1, r2, term2, info2, n,
-	                                                                                    agent_reward, opp_reward, done);
+	                                                                                    agent_reward, opp_reward, done, mode);
 	g_launches++;
 	return (int)cudaGetLastError();
 }

@@ -226,7 +226,8 @@ class SplendorVecEnv:
         self._is_reset = True
 
     # ------------------------------------------------------------------ dual step (self-play turn)
-    def dual_step(self, agent_actions: torch.Tensor, opponent_policy: Callable[[torch.Tensor, torch.Tensor], torch.Tensor]):
+    def dual_step(self, agent_actions: torch.Tensor, opponent_policy: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+                  reward_mode: str = "native"):
         """``DualStepNativeWrapper.dual_step`` (wrappers/dual_step_native.py:90-193), batched.
 
         Phase 1: every env applies the agent's (player 0) action.  Phase 2: envs still running apply
@@ -254,6 +255,6 @@ class SplendorVecEnv:
             L.check(self.lib.spl_dual_combine(D["r1"].data_ptr(), D["t1"].data_ptr(), D["i1"].data_ptr(), self.reward.data_ptr(),
                                               self._terminated.data_ptr(), self.info_bits.data_ptr(), self.n,
                                               D["agent_r"].data_ptr(), D["opp_r"].data_ptr(), D["done"].data_ptr(),
-                                              self._stream()), "spl_dual_combine")
+                                              {"native": 0, "selfplay": 1}[reward_mode], self._stream()), "spl_dual_combine")
         info = {"action_mask": self.mask, "to_play": self.obs[:, 294], "info_bits_agent": D["i1"], "info_bits_opponent": self.info_bits}
         return obs, D["agent_r"], obs, D["opp_r"], D["done"].view(torch.bool), info

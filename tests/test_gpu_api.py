@@ -1,0 +1,261 @@
+"""The reference's single-environment API surface (SplendorEnv, engine functions, wrappers) on top of the CUDA
+kernels.  These tests restate what the reference's own test-suite pins (splendor_gym/tests/*.py; SURVEY.md
+section 4), against this package's import paths, and tie the facade to the batched path."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def first_legal(mask):
+    legal = np.flatnonzero(mask)
+    return int(legal[0]) if len(legal) else 0
+
+
+# ----------------------------------------------------------------------------- engine functions
+def test_initial_state_matches_reference_fingerprints():
+    """initial_state(seed) boards / nobles / deck tops / obs hash as produced by the reference."""
+    from splendor_gym_b200.engine import initial_state, legal_moves
+    from splendor_gym_b200.engine.encode import TOTAL_ACTIONS, encode_observation
+
+    want = {
+        0: ([[24, 26, 2, 16], [54, 67, 56, 48], [86, 85, 73, 79]], [1007, 1009, 1005], [32, 41, 89], "acccb83d866e5f0c"),
+        42: ([[7, 1, 17, 15], [51, 67, 69, 59], [81, 75, 89, 87]], [1004, 1009, 1001], [14, 48, 76], "1e1673d87f5d6bc3"),
+    }
+    for seed, (board, nobles, tops, sha) in want.items():
+        s = initial_state(seed=seed)
+        assert [[c.id for c in s.board[t]] for t in (1, 2, 3)] == board
+        assert [n.id for n in s.nobles] == nobles
+        assert [s.decks[t][-1].id for t in (1, 2, 3)] == tops
+        assert hashlib.sha256(encode_observation(s).tobytes()).hexdigest()[:16] == sha
+        m = legal_moves(s)
+        assert len(m) == TOTAL_ACTIONS and any(m)
+        assert s.bank == [4, 4, 4, 4, 4, 5] and s.to_play == 0 and s.turn_count == 1 and s.move_count == 0
+
+
+def test_take_actions_move_tokens_and_keep_turn_count():
+    from splendor_gym_b200.engine import apply_action, initial_state, legal_moves
+
+    s = initial_state(seed=1)
+    a = first_legal(legal_moves(s))
+    before = sum(s.bank)
+    s2 = apply_action(s, a)
+    assert a < 10 and sum(s2.bank) == before - 3
+    assert s2.turn_count == s.turn_count and s2.move_count == 1 and s2.to_play == 1
+    assert sum(s.bank) == before  # apply_action is pure: the input state is untouched
+    s3 = apply_action(s, 12)
+    assert sum(s3.bank) == before - 2 and s3.players[0].tokens[2] == 2
+    with pytest.raises(ValueError):
+        apply_action(s, 45)
+
+
+def test_mask_invariants():
+    from splendor_gym_b200.engine import initial_state, legal_moves
+
+    s = initial_state(seed=7)
+    s.bank[1] = 3
+    s.board[2][3] = None
+    s.decks[3].clear()
+    m = legal_moves(s)
+    p = s.players[s.to_play]
+    for ci in range(5):
+        assert (m[10 + ci] == 1) == (s.bank[ci] >= 4)
+    for tier in (1, 2, 3):
+        assert (m[39 + tier - 1] == 1) == (len(s.decks[tier]) > 0 and len(p.reserved) < 3)
+        for slot in range(4):
+            if s.board[tier][slot] is None:
+                assert m[15 + (tier - 1) * 4 + slot] == 0 and m[27 + (tier - 1) * 4 + slot] == 0
+    assert m[15 + 4 + 3] == 0 and m[27 + 4 + 3] == 0 and m[41] == 0
+
+
+def test_token_limit_after_oversized_hand():
+    """Hands above the limit (as the reference's tests inject them) come back to exactly 10, non-gold first."""
+    from splendor_gym_b200.engine import apply_action, initial_state
+
+    s = initial_state(seed=0)
+    s.players[0].tokens = [5, 5, 5, 5, 5, 0]
+    s2 = apply_action(s, 0)
+    assert sum(s2.players[0].tokens) == 10
+    g = next(c for c in load_golden("edge_cases.json") if c["name"] == "token_limit_25_tokens")
+    assert s2.players[0].tokens == g["row_out"][6:12] and s2.bank == g["row_out"][0:6]
+
+
+# ----------------------------------------------------------------------------- SplendorEnv facade
+def test_env_reset_step_types_and_seeding():
+    from splendor_gym_b200.envs import SplendorEnv
+
+    env = SplendorEnv(num_players=2)
+    assert env.action_space.n == 45 and env.observation_space.shape == (297,)
+    for rec in load_golden("env_seeding.json"):  # gymnasium's PCG64 seeding path, pinned from the reference run
+        obs, info = env.reset(seed=rec["seed"])
+        assert obs.shape == (297,) and obs.dtype == np.int32
+        assert info["action_mask"].shape == (45,) and info["action_mask"].dtype == np.int8 and info["to_play"] == 0
+        assert [c.id for c in env.state.board[1]] == rec["tier1_board"]
+    obs, r, term, trunc, info = env.step(first_legal(info["action_mask"]))
+    assert isinstance(r, float) and isinstance(term, bool) and trunc is False and "action_mask" in info
+    with pytest.raises(NotImplementedError):
+        SplendorEnv(num_players=3)
+
+
+def test_env_determinism_and_random_play():
+    from splendor_gym_b200.envs import SplendorEnv
+
+    e1, e2 = SplendorEnv(), SplendorEnv()
+    o1, i1 = e1.reset(seed=42)
+    o2, i2 = e2.reset(seed=42)
+    assert np.array_equal(o1, o2)
+    rng = np.random.RandomState(0)
+    for _ in range(50):
+        legal = np.flatnonzero(i1["action_mask"])
+        a = int(legal[rng.randint(len(legal))]) if len(legal) else 0
+        o1, r1, t1, _, i1 = e1.step(a)
+        o2, r2, t2, _, i2 = e2.step(a)
+        assert np.array_equal(o1, o2) and (r1, t1) == (r2, t2) and np.array_equal(i1["action_mask"], i2["action_mask"])
+        if t1:
+            break
+
+
+def test_env_illegal_action_and_errors():
+    from splendor_gym_b200.envs import SplendorEnv
+
+    env = SplendorEnv()
+    with pytest.raises(AssertionError):
+        env.step(0)
+    obs, info = env.reset(seed=3)
+    illegal = int(np.flatnonzero(info["action_mask"] == 0)[0])
+    before = env.state.move_count
+    obs2, r, term, trunc, info2 = env.step(illegal)
+    assert r == pytest.approx(-0.01) and not term and info2.get("illegal_action") and env.state.move_count == before
+    assert np.array_equal(obs, obs2) and np.array_equal(info["action_mask"], info2["action_mask"])
+    with pytest.raises(ValueError):
+        env.step(45)
+    env.state.game_over = True
+    with pytest.raises(RuntimeError):
+        env.step(0)
+
+
+def test_env_no_legal_move_draw():
+    from splendor_gym_b200.engine import legal_moves
+    from splendor_gym_b200.envs import SplendorEnv
+
+    env = SplendorEnv()
+    env.reset(seed=0)
+    env.state.bank[:] = [0, 0, 0, 0, 0, 0]
+    p = env.state.players[env.state.to_play]
+    p.tokens[:] = [10, 0, 0, 0, 0, 0]
+    p.reserved = env.state.decks[1][:3]
+    for t in (1, 2, 3):
+        env.state.board[t] = [None, None, None, None]
+    assert not any(legal_moves(env.state))
+    obs, r, term, trunc, info = env.step(0)
+    assert term and r == 0 and env.state.winner_index is None and info.get("draw") and "final_rewards" not in info
+    assert not info["action_mask"].any()
+
+
+def test_env_reduced_take3():
+    from splendor_gym_b200.engine import legal_moves
+    from splendor_gym_b200.envs import SplendorEnv
+
+    env = SplendorEnv()
+    env.reset(seed=123)
+    env.state.bank[:] = [1, 0, 2, 0, 0, 0]
+    m = legal_moves(env.state)
+    assert [i for i in range(10) if m[i]] == [0, 3, 4]
+    env.step(0)
+    last = env.state.players[1 - env.state.to_play]
+    assert last.tokens[0] + last.tokens[2] == 2
+    env.reset(seed=123)
+    env.state.bank[:] = [0, 0, 0, 0, 3, 0]
+    m = legal_moves(env.state)
+    assert [i for i in range(10) if m[i]] == [2, 4, 5, 7, 8, 9]
+    env.step(2)
+    assert env.state.players[1 - env.state.to_play].tokens[4] == 1
+
+
+def test_observation_layout_and_hidden_reservation():
+    """Section offsets (bank 0:6, me 6:19, opponent 19:32, board 32:188, reserved 188:272, nobles 272:290, tail
+    290:297); my reserved cards always carry revealed=1; the opponent's blind reservation is 14 zeros."""
+    from splendor_gym_b200.envs import SplendorEnv
+
+    env = SplendorEnv()
+    obs, info = env.reset(seed=9)
+    assert obs[0:6].tolist() == [4, 4, 4, 4, 4, 5] and obs[6:32].sum() == 0
+    assert obs[290:293].tolist() == [36, 26, 16] and obs[293:297].tolist() == [1, 0, 0, 0]
+    assert all(obs[32 + 13 * k] == 1 for k in range(12)) and all(obs[272 + 6 * k] == 1 for k in range(3))
+    obs, *_ = env.step(39)  # P0 reserves blind (tier 1)
+    assert obs[18 + 13] == 1 and obs[230:244].sum() == 0  # P1 sees the count, not the card
+    obs, *_ = env.step(27)  # P1 reserves the visible tier-1 slot 0
+    own = obs[188:202]
+    assert own[0] == 1 and own[13] == 1 and own[1] == 1  # P0 sees its own hidden card, tier 1
+    theirs = obs[230:244]
+    assert theirs[0] == 1 and theirs[13] == 1  # P1's reservation came from the board: public
+
+
+# ----------------------------------------------------------------------------- wrappers
+def test_selfplay_and_dual_step_wrappers_against_batched_path():
+    """Single-env wrappers driven by Python callbacks == SplendorVecEnv.dual_step with the same policies."""
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200.envs import SplendorEnv
+    from splendor_gym_b200.wrappers import DualStepNativeWrapper, SelfPlayWrapper, vec_selfplay_step
+
+    def opp(obs, info):  # deterministic opponent: highest legal action index
+        legal = np.flatnonzero(info["action_mask"])
+        return int(legal[-1]) if len(legal) else 0
+
+    def vec_opp(obs, mask):
+        idx = torch.arange(45, device=mask.device, dtype=torch.int32)
+        return torch.where(mask > 0, idx, torch.full_like(idx, -1)).max(dim=1).values.clamp(min=0).to(torch.int32)
+
+    seeds = [11, 12, 13, 14]
+    engine_seeds = [int(np.random.Generator(np.random.PCG64(np.random.SeedSequence(s))).integers(0, 2**31 - 1)) for s in seeds]
+    for mode in ("native", "selfplay"):
+        vec = SplendorVecEnv(len(seeds), shuffle="mt19937", autoreset=False)
+        vobs, vinfo = vec.reset(seeds=torch.tensor(engine_seeds, dtype=torch.int64))
+        singles = []
+        for s in seeds:
+            base = SplendorEnv()
+            w = (DualStepNativeWrapper if mode == "native" else SelfPlayWrapper)(base, opponent_policy=opp, random_starts=True)
+            o, i = w.reset(seed=s)
+            singles.append([w, o, i, False])
+        for it in range(80):
+            acts = [first_legal(x[2]["action_mask"]) for x in singles]
+            alive = [not x[3] for x in singles]
+            if not any(alive):
+                break
+            a = torch.tensor(acts, dtype=torch.int32, device="cuda")
+            if mode == "native":
+                o, ar, _, orr, done, _ = vec.dual_step(a, vec_opp)
+            else:
+                o, ar, done, _, _ = vec_selfplay_step(vec, a, vec_opp)
+            for k, x in enumerate(singles):
+                if x[3]:
+                    continue
+                if mode == "native":
+                    so, sr, _, sor, sd, si = x[0].dual_step(acts[k])
+                    assert float(orr[k]) == pytest.approx(sor)
+                else:
+                    so, sr, sd, _, si = x[0].step(acts[k])
+                assert np.array_equal(o[k].cpu().numpy(), so) and float(ar[k]) == pytest.approx(sr) and bool(done[k]) == sd
+                assert np.array_equal(vec.mask[k].cpu().numpy(), si["action_mask"])
+                x[1], x[2], x[3] = so, si, sd
+        assert all(x[3] for x in singles)
+
+
+def test_random_opponent_helper():
+    from splendor_gym_b200.wrappers import random_opponent
+
+    m = np.zeros(45, np.int8)
+    assert random_opponent(None, {"action_mask": m}) == 0 and random_opponent(None, {}) == 0
+    m[[3, 17]] = 1
+    assert {random_opponent(None, {"action_mask": m}) for _ in range(50)} == {3, 17}
