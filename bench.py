@@ -228,9 +228,9 @@ def run_b200(args):
     from splendor_gym_b200 import SplendorVecEnv
     from splendor_gym_b200 import _lib as L
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from splendor_gym_b200.distributed import rank_world
+
+    rank, world, local = rank_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local)

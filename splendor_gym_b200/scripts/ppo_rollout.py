@@ -1,0 +1,112 @@
+"""Rollout collection of ppo_splendor.py:202-297 with the MLP policy in the loop (BASELINE config 3), with the
+environment on the device: observations / masks never leave HBM, the per-env Python loop and both host<->device
+copies of the reference (:221-225, :235-250) are gone.  The policy network is the reference's architecture
+(ppo_splendor.py:41-59: 297 -> 256 -> 256 -> {45, 1}, tanh) in plain PyTorch -- it is the caller of the hot path,
+not part of it.  The agent samples from the masked categorical (:27-38), the opponent plays the masked argmax
+of the same network (scripts/eval_suite.py:131-141), turns are DualStepNativeWrapper.dual_step (:90-193).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import time
+
+import torch
+import torch.nn as nn
+
+from ..vec_env import SplendorVecEnv
+
+
+class ActorCritic(nn.Module):
+    def __init__(self, obs_dim: int = 297, act_dim: int = 45):
+        super().__init__()
+        self.critic = nn.Sequential(nn.Linear(obs_dim, 256), nn.Tanh(), nn.Linear(256, 256), nn.Tanh(), nn.Linear(256, 1))
+        self.actor = nn.Sequential(nn.Linear(obs_dim, 256), nn.Tanh(), nn.Linear(256, 256), nn.Tanh(), nn.Linear(256, act_dim))
+
+
+def masked_logits(logits: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Illegal actions -> -inf; rows without any legal action are left unmasked (ppo_splendor.py:27-38)."""
+    illegal = mask < 1
+    any_legal = (~illegal).any(dim=1, keepdim=True)
+    return torch.where(illegal & any_legal, torch.full_like(logits, float("-inf")), logits)
+
+
+@torch.no_grad()
+def collect(env: SplendorVecEnv, net: ActorCritic, num_steps: int, buffers=None, dtype=torch.float32):
+    """num_steps dual-steps for every env; fills (and returns) rollout buffers shaped like ppo_splendor.py:210-217."""
+    n, dev = env.n, env.device
+    if buffers is None:
+        buffers = dict(
+            obs=torch.zeros((num_steps, n, 297), dtype=torch.int32, device=dev), masks=torch.zeros((num_steps, n, 45), dtype=torch.int8, device=dev),
+            actions=torch.zeros((num_steps, n), dtype=torch.int32, device=dev), logprobs=torch.zeros((num_steps, n), device=dev),
+            values=torch.zeros((num_steps, n), device=dev), rewards=torch.zeros((num_steps, n), device=dev),
+            terminals=torch.zeros((num_steps, n), dtype=torch.bool, device=dev),
+        )
+
+    def opponent(obs, mask):  # model_greedy_policy_from: argmax of the masked logits
+        return masked_logits(net.actor(obs.to(dtype)).float(), mask).argmax(dim=1).to(torch.int32)
+
+    for t in range(num_steps):
+        x = env.obs.to(dtype)
+        logits = masked_logits(net.actor(x).float(), env.mask)
+        dist = torch.distributions.Categorical(logits=logits)
+        action = dist.sample()
+        buffers["obs"][t].copy_(env.obs)
+        buffers["masks"][t].copy_(env.mask)
+        buffers["actions"][t].copy_(action)
+        buffers["logprobs"][t].copy_(dist.log_prob(action))
+        buffers["values"][t].copy_(net.critic(x).float().squeeze(1))
+        _, agent_r, _, _, done, _ = env.dual_step(action.to(torch.int32), opponent)
+        buffers["rewards"][t].copy_(agent_r)
+        buffers["terminals"][t].copy_(done)
+    return buffers
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--num-envs", type=int, default=262144)
+    ap.add_argument("--num-steps", type=int, default=128)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--checkpoint", default=None, help="state_dict of the reference's ActorCritic (runs/ppo_splendor/ppo_splendor_latest.pt)")
+    ap.add_argument("--bf16", action="store_true")
+    ap.add_argument("--repeats", type=int, default=2)
+    args = ap.parse_args(argv)
+    torch.manual_seed(args.seed)
+    dev = torch.device("cuda")
+    net = ActorCritic().to(dev)
+    if args.checkpoint:
+        net.load_state_dict(torch.load(args.checkpoint, map_location=dev))
+    dtype = torch.bfloat16 if args.bf16 else torch.float32
+    net = net.to(dtype).eval()
+    env = SplendorVecEnv(args.num_envs, seed=args.seed, shuffle="philox", autoreset=True)
+    env.reset()
+    # rollout buffers in chunks so that 262,144 envs x 128 steps (40 GB of int32 observations) is not required at once
+    chunk = max(1, min(args.num_steps, int(8e9 // (args.num_envs * 1188))))
+    buf = collect(env, net, chunk, dtype=dtype)
+    torch.cuda.synchronize()
+    env_ms = 0.0
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps = 0
+    for _ in range(args.repeats):
+        done = 0
+        while done < args.num_steps:
+            k = min(chunk, args.num_steps - done)
+            collect(env, net, k, buffers=buf, dtype=dtype)
+            done += k
+            steps += k
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    agent_steps = steps * args.num_envs
+    out = {"config": "PPO-MLP self-play rollout (BASELINE configs[2])", "num_envs": args.num_envs, "dual_steps": steps,
+           "agent_steps_per_s": agent_steps / (ms * 1e-3), "env_steps_per_s_upper": 2 * agent_steps / (ms * 1e-3),
+           "ms_per_dual_step": ms / steps, "policy_dtype": str(dtype), "wall_s": time.perf_counter() - t0,
+           "episode_stats": env.stats.cpu().tolist()}
+    print(json.dumps(out))
+    return out
+
+
+if __name__ == "__main__":
+    main()

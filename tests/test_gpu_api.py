@@ -259,3 +259,38 @@ def test_random_opponent_helper():
     assert random_opponent(None, {"action_mask": m}) == 0 and random_opponent(None, {}) == 0
     m[[3, 17]] = 1
     assert {random_opponent(None, {"action_mask": m}) for _ in range(50)} == {3, 17}
+
+
+# ----------------------------------------------------------------------------- scripts (callers of the hot path)
+def test_random_rollout_script(capsys):
+    """scripts/random_rollout.py (BASELINE config 1) on the facade and in its batched form."""
+    from splendor_gym_b200.scripts import random_rollout
+
+    np.random.seed(0)
+    random_rollout.main(["--episodes", "2", "--seed", "0"])
+    out = capsys.readouterr().out
+    assert "Episode 0: steps=" in out and "Wins:" in out
+    st = random_rollout.main(["--episodes", "1", "--envs", "512"])
+    assert st["episodes"] >= 512 and st["p0_wins"] + st["p1_wins"] + st["tie_draws"] + st["limit_draws"] + st["nolegal_draws"] == st["episodes"]
+
+
+def test_ppo_rollout_collection_small():
+    """Rollout collection with the MLP policy in the loop (BASELINE config 3, tiny): buffers are filled, actions
+    are legal under the stored masks, agent is always player 0, rewards only at episode ends."""
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200.scripts.ppo_rollout import ActorCritic, collect
+
+    torch.manual_seed(0)
+    net = ActorCritic().cuda().eval()
+    env = SplendorVecEnv(2048, seed=4, shuffle="philox", autoreset=True)
+    env.reset()
+    buf = collect(env, net, 96)
+    legal = buf["masks"].gather(2, buf["actions"].long().unsqueeze(2)).squeeze(2)
+    has_move = buf["masks"].sum(dim=2) > 0
+    assert bool((legal[has_move] == 1).all())
+    assert bool((buf["obs"][:, :, 294] == 0).all())  # the agent always observes as player 0
+    r, d = buf["rewards"], buf["terminals"]
+    assert bool((r[~d] == 0).all()) and int(d.sum()) > 100
+    vals = set(torch.unique(r[d]).cpu().tolist())
+    assert vals <= {-1.0, 0.0, 1.0, pytest.approx(-0.1)} or all(abs(v) <= 1.0 for v in vals)
+    assert int(env.stats[0]) == int(d.sum())
