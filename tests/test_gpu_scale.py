@@ -1,7 +1,7 @@
 """Parity volume: random-policy games replayed bit-exactly against the oracle -- observations, masks, rewards,
 terminations, info bits after EVERY step and the full state periodically -- in MT19937 mode (decks identical to the
-reference's initial_state).  Default: ~1e5 finished games (about half a minute on the GPU box); with
-SPL_SCALE_GAMES=1000000 the north-star volume of >= 1e6 games (a few minutes; result logged in profiles/)."""
+reference's initial_state).  Default: the north-star volume of >= 1e6 finished games (~8e7 env-steps; about half a minute on the GPU box, result
+logged in profiles/r01_parity_volume.log); SPL_SCALE_GAMES overrides the target."""
 import os
 import time
 
@@ -17,7 +17,7 @@ def test_parity_volume(oracle):
         pytest.skip("no CUDA device")
     from splendor_gym_b200 import SplendorVecEnv
 
-    target = int(os.environ.get("SPL_SCALE_GAMES", "100000"))
+    target = int(os.environ.get("SPL_SCALE_GAMES", "1000000"))
     n = 65536
     env = SplendorVecEnv(n, seed=777, shuffle="mt19937", autoreset=True)
     ref = oracle.OracleVec(n, seed_base=777)
