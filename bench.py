@@ -159,14 +159,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU legs
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_rollout(envs: int, seconds: float, threads: int | None = None):
     """Oracle port of the reference engine on the host cores: random-legal lock-step rollout with same-step
     auto-reset, full step+mask+obs per env-step. Returns (steps_per_s, threads, description)."""
     from oracle import oracle as O
 
     O.build()
-    if threads:
-        O.set_num_threads(threads)
+    O.set_num_threads(threads or host_threads())  # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
     nthreads = O.num_threads()
     v = O.OracleVec(envs, seed_base=0)
     v.reset()
@@ -190,6 +196,7 @@ def run_reference(args):
     from oracle import oracle as O
 
     O.build()
+    O.set_num_threads(host_threads())
     nthreads = O.num_threads()
     envs = args.envs
     chunk = 8  # lock-steps per bench step: a bounded sample of the rollout segment
@@ -308,12 +315,19 @@ def run_b200(args):
         L.check(lib.spl_timing_enable(1))
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    side = torch.cuda.Stream() if world > 1 else None
     e0.record()
     for _ in range(K):
         run()
-        if world > 1:  # episode statistics are the only cross-GPU traffic (NCCL all-reduce of 8 int64)
-            stats_host.copy_(env.stats)
-            dist.all_reduce(stats_host)
+        if world > 1:
+            # episode statistics are the only cross-GPU traffic: one NCCL all-reduce of 8 int64 per segment, issued
+            # on a side stream so that it overlaps the next segment instead of serialising with it
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                stats_host.copy_(env.stats)
+                dist.all_reduce(stats_host)
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(side)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)

@@ -161,6 +161,25 @@ int spl_dual_combine(const float *r1, const uint8_t *term1, const uint8_t *info1
                      const uint8_t *info2, int64_t n, float *agent_reward, float *opp_reward, uint8_t *done, int mode,
                      void *stream);
 
+/* ---- callers on either side of the step path, kept on the device ---- */
+
+/* scripted opponents of scripts/eval_suite.py over (obs [n][297], mask [n][45]) */
+#define SPL_BOT_RANDOM 0         /* wrappers/selfplay.py:66-73 random_opponent */
+#define SPL_BOT_GREEDY_V1 1      /* scripts/eval_suite.py:10-30 greedy_opponent_v1 */
+#define SPL_BOT_BASIC_PRIORITY 2 /* scripts/eval_suite.py:33-77 basic_priority_opponent (np.random.choice -> Philox stream) */
+#define SPL_BOT_GREEDY_V2 3      /* scripts/eval_suite.py:80-128 greedy_opponent_v2_factory(env_ref) (bank read from obs[0:5]) */
+int spl_scripted_action(const int32_t *obs, const int8_t *mask, int64_t n, int kind, uint64_t env_offset, uint64_t key,
+                        uint64_t t, int32_t *actions, void *stream);
+
+/* masked categorical over logits [n][45] (ppo_splendor.py:27-38,54-59): mode 0 = sample (Philox inverse CDF),
+ * mode 1 = argmax (scripts/eval_suite.py:131-141 model_greedy_policy_from).  logprob / entropy nullable. */
+int spl_masked_sample(const float *logits, const int8_t *mask, int64_t n, int mode, uint64_t env_offset, uint64_t key,
+                      uint64_t t, int32_t *actions, float *logprob, float *entropy, void *stream);
+
+/* generalised advantage estimation over step-major [T][n] buffers (ppo_splendor.py:299-314) */
+int spl_gae(const float *rewards, const float *values, const uint8_t *terminals, const float *last_values, int32_t T,
+            int64_t n, float gamma, float lam, float *advantages, float *returns, void *stream);
+
 const char *spl_error_string(int code);
 int spl_version(void);
 /* host copy of the token-return table (SPL_RET_TABLE_LEN x u64) for tests */

@@ -15,6 +15,7 @@ Files written:
                       (obs, mask, state row, reward, terminated, info bits) + a few full vectors
   edge_cases.json     hand-built states mirroring the reference's own tests (tests/utils.py style
                       mutation of env.state): full input row, action, and every output
+  bots.json           (obs, mask) states + the decisions of the scripted opponents of scripts/eval_suite.py
 """
 from __future__ import annotations
 
@@ -389,6 +390,39 @@ def gen_edges():
     dump("edge_cases.json", out)
 
 
+
+
+# ----------------------------------------------------------------------------- bots.json
+def gen_bots():
+    """(obs, mask) states from reference games + the decision of each scripted opponent of scripts/eval_suite.py.
+    Deterministic bots: the action.  basic_priority (np.random.choice): the support set over 64 RNG seeds."""
+    from splendor_gym.scripts import eval_suite as ES
+
+    out = []
+    rng = np.random.RandomState(5)
+    for g in range(24):
+        env = env_from_state(R.initial_state(seed=1000 + g))
+        obs = ENC.encode_observation(env.state)
+        info = {"action_mask": np.array(R.legal_moves(env.state), dtype=np.int8)}
+        v2 = ES.greedy_opponent_v2_factory(env)
+        bots = [ES.greedy_opponent_v1, ES.basic_priority_opponent, v2]
+        for t in range(300):
+            mask = info["action_mask"]
+            if t % 6 == g % 6:
+                support = set()
+                for sd in range(64):
+                    np.random.seed(sd)
+                    support.add(int(ES.basic_priority_opponent(obs, info)))
+                out.append({"obs": obs.tolist(), "mask": mask.tolist(), "greedy_v1": int(ES.greedy_opponent_v1(obs, info)),
+                            "greedy_v2": int(v2(obs, info)), "basic_support": sorted(support)})
+            np.random.seed(int(rng.randint(1 << 30)))
+            a = bots[(g + t) % 3](obs, info) if mask.any() else 0
+            obs, r, term, trunc, info = env.step(int(a))
+            if term:
+                break
+    dump("bots.json", out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_mt()
@@ -397,3 +431,4 @@ if __name__ == "__main__":
     gen_env_seeding()
     gen_games()
     gen_edges()
+    gen_bots()

@@ -35,8 +35,10 @@ STAT_NAMES = ("episodes", "p0_wins", "p1_wins", "tie_draws", "limit_draws", "nol
 EXPORTS = (
     "spl_init", "spl_reset", "spl_step", "spl_observe", "spl_random_action", "spl_export_state", "spl_import_state",
     "spl_dual_combine", "spl_error_string", "spl_version", "spl_host_ret_table", "spl_launch_count",
-    "spl_timing_enable", "spl_timing_read", "spl_rollout_random",
+    "spl_timing_enable", "spl_timing_read", "spl_rollout_random", "spl_scripted_action", "spl_masked_sample", "spl_gae",
 )
+
+BOT_RANDOM, BOT_GREEDY_V1, BOT_BASIC_PRIORITY, BOT_GREEDY_V2 = 0, 1, 2, 3
 
 
 class SplEnvs(C.Structure):
@@ -87,6 +89,12 @@ def load():
     L.spl_step.argtypes = [C.POINTER(SplEnvs), C.POINTER(SplStepIO), vp]
     L.spl_rollout_random.restype = C.c_int
     L.spl_rollout_random.argtypes = [C.POINTER(SplEnvs), C.POINTER(SplStepIO), C.c_int32, vp]
+    L.spl_scripted_action.restype = C.c_int
+    L.spl_scripted_action.argtypes = [vp, vp, i64, C.c_int, u64, u64, u64, vp, vp]
+    L.spl_masked_sample.restype = C.c_int
+    L.spl_masked_sample.argtypes = [vp, vp, i64, C.c_int, u64, u64, u64, vp, vp, vp, vp]
+    L.spl_gae.restype = C.c_int
+    L.spl_gae.argtypes = [vp, vp, vp, vp, C.c_int32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.spl_observe.restype = C.c_int
     L.spl_observe.argtypes = [C.POINTER(SplEnvs), vp, vp, vp]
     L.spl_random_action.restype = C.c_int

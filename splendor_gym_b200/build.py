@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libsplendor_b200.so")
-SOURCES = ["spl_kernels.cu"]
-DEPS = ["spl_kernels.cu", "spl_core.cuh", "spl_tables_host.h", "../../include/splendor_b200.h", "../../include/spl_tables.h"]
+SOURCES = ["spl_kernels.cu", "spl_policy.cu"]
+DEPS = ["spl_kernels.cu", "spl_policy.cu", "spl_core.cuh", "spl_tables_host.h", "../../include/splendor_b200.h", "../../include/spl_tables.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -777,7 +777,7 @@ static int g_num_sms = 0;
 static int g_occ[3][2];  // [kernel: step, observe, rollout][wpc 1 / 4] resident CTAs per SM
 static uint64_t g_host_ret[SPL_RET_TABLE_LEN];
 static bool g_host_ret_built = false;
-static int64_t g_launches = 0;
+int64_t g_launches = 0;  // also bumped by spl_policy.cu
 // optional per-launch timing of the step kernel (bench.py roofline leg): CUDA events recorded on the
 // caller's stream right around the kernel
 #define SPL_TIMING_POOL 4096

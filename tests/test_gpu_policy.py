@@ -1,0 +1,106 @@
+"""Device-side callers of the step path: scripted opponents vs the decisions the
+reference's bots made on the same (obs, mask) (tests/golden/bots.json), masked categorical sampling vs
+torch.distributions, GAE vs a float64 restatement of ppo_splendor.py:307-314."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_scripted_bots_match_reference_decisions():
+    from splendor_gym_b200.policy import scripted_action
+
+    recs = load_golden("bots.json")
+    obs = torch.tensor([r["obs"] for r in recs], dtype=torch.int32, device="cuda")
+    mask = torch.tensor([r["mask"] for r in recs], dtype=torch.int8, device="cuda")
+    g1 = scripted_action(obs, mask, "greedy_v1").cpu().tolist()
+    g2 = scripted_action(obs, mask, "greedy_v2").cpu().tolist()
+    assert g1 == [r["greedy_v1"] for r in recs]
+    assert g2 == [r["greedy_v2"] for r in recs]
+    seen = [set() for _ in recs]
+    for t in range(48):
+        b = scripted_action(obs, mask, "basic", t=t).cpu().tolist()
+        rnd = scripted_action(obs, mask, "random", t=t).cpu().tolist()
+        for i, r in enumerate(recs):
+            assert b[i] in r["basic_support"], (i, b[i], r["basic_support"])
+            assert r["mask"][rnd[i]] == 1 or sum(r["mask"]) == 0
+            seen[i].add(b[i])
+    # the random tie-breaks cover the whole support the reference's np.random.choice can produce
+    assert all(seen[i] == set(r["basic_support"]) for i, r in enumerate(recs) if len(r["basic_support"]) <= 4)
+
+
+def test_bots_drive_dual_step():
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200.policy import bot_policy, scripted_action
+
+    env = SplendorVecEnv(4096, seed=12, shuffle="philox", autoreset=True)
+    env.reset()
+    opp = bot_policy("greedy_v1")
+    for t in range(120):
+        a = scripted_action(env.obs, env.mask, "basic", t=t)
+        env.dual_step(a, opp)
+    st = env.stats.cpu().tolist()
+    assert st[0] > 2000 and st[1] + st[2] + st[3] + st[4] + st[5] == st[0]
+
+
+def test_masked_sample_against_torch():
+    from splendor_gym_b200.policy import masked_sample
+
+    torch.manual_seed(0)
+    n = 4096
+    logits = torch.randn(n, 45, device="cuda") * 2
+    mask = (torch.rand(n, 45, device="cuda") < 0.3).to(torch.int8)
+    mask[:7] = 0  # rows without a legal action stay unmasked (ppo_splendor.py:36-37)
+    m = mask.bool()
+    any_legal = m.any(dim=1, keepdim=True)
+    ml = torch.where(~m & any_legal, torch.full_like(logits, float("-inf")), logits)
+    dist = torch.distributions.Categorical(logits=ml)
+    a, lp, ent = masked_sample(logits, mask, greedy=True, want_entropy=True)
+    assert torch.equal(a.long(), ml.argmax(dim=1))
+    assert torch.allclose(lp, dist.log_prob(a.long()), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(ent, dist.entropy(), atol=1e-4, rtol=1e-4)
+    a, lp, _ = masked_sample(logits, mask, t=3)
+    assert bool((ml.gather(1, a.long().view(-1, 1)) > float("-inf")).all())
+    assert torch.allclose(lp, dist.log_prob(a.long()), atol=1e-5, rtol=1e-5)
+    # distribution: one fixed row sampled many times with different counters
+    row_l = logits[100:101].repeat(20000, 1).contiguous()
+    row_m = mask[100:101].repeat(20000, 1).contiguous()
+    s, _, _ = masked_sample(row_l, row_m, t=9, want_logprob=False)
+    counts = torch.bincount(s.long(), minlength=45).float().cpu().numpy()
+    p = dist.probs[100].cpu().numpy()
+    exp = p * 20000
+    sel = exp > 5
+    chi2 = float(((counts[sel] - exp[sel]) ** 2 / exp[sel]).sum())
+    assert counts[~(p > 0)].sum() == 0 and chi2 < 4 * sel.sum() + 20
+
+
+def test_gae_against_reference_formula():
+    from splendor_gym_b200.policy import gae
+
+    rng = np.random.RandomState(1)
+    T, n, gamma, lam = 128, 3000, 0.99, 0.95
+    rewards = (rng.rand(T, n) < 0.02) * rng.choice([-1.0, 1.0, -0.1], size=(T, n))
+    terms = rewards != 0
+    values = rng.randn(T, n).astype(np.float32)
+    last = rng.randn(n).astype(np.float32)
+    adv = np.zeros((T, n))
+    lastgaelam = np.zeros(n)
+    for t in reversed(range(T)):  # ppo_splendor.py:307-313
+        nonterm = 1.0 - terms[t]
+        nextv = last if t == T - 1 else values[t + 1]
+        delta = rewards[t] + gamma * nextv * nonterm - values[t]
+        adv[t] = lastgaelam = delta + gamma * lam * nonterm * lastgaelam
+    ret = adv + values
+    a, r = gae(torch.tensor(rewards, dtype=torch.float32).cuda(), torch.tensor(values).cuda(), torch.tensor(terms).cuda(),
+               torch.tensor(last).cuda(), gamma, lam)
+    assert np.allclose(a.cpu().numpy(), adv, atol=2e-5, rtol=1e-5)
+    assert np.allclose(r.cpu().numpy(), ret, atol=2e-5, rtol=1e-5)
