@@ -24,11 +24,13 @@ class ActorCritic(nn.Module):
         self.actor = nn.Sequential(nn.Linear(obs_dim, 256), nn.Tanh(), nn.Linear(256, 256), nn.Tanh(), nn.Linear(256, act_dim))
 
 
-def masked_logits(logits: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    """Illegal actions -> -inf; rows without any legal action are left unmasked (ppo_splendor.py:27-38)."""
-    illegal = mask < 1
-    any_legal = (~illegal).any(dim=1, keepdim=True)
-    return torch.where(illegal & any_legal, torch.full_like(logits, float("-inf")), logits)
+def advantages(env: SplendorVecEnv, net: "ActorCritic", buffers, gamma: float = 0.99, gae_lambda: float = 0.95, dtype=torch.float32):
+    """GAE over the collected segment on the device (ppo_splendor.py:299-314)."""
+    from ..policy import gae
+
+    with torch.no_grad():
+        last_values = net.critic(env.obs.to(dtype)).float().squeeze(1)
+    return gae(buffers["rewards"], buffers["values"], buffers["terminals"], last_values, gamma, gae_lambda)
 
 
 @torch.no_grad()
@@ -43,20 +45,21 @@ def collect(env: SplendorVecEnv, net: ActorCritic, num_steps: int, buffers=None,
             terminals=torch.zeros((num_steps, n), dtype=torch.bool, device=dev),
         )
 
-    def opponent(obs, mask):  # model_greedy_policy_from: argmax of the masked logits
-        return masked_logits(net.actor(obs.to(dtype)).float(), mask).argmax(dim=1).to(torch.int32)
+    from ..policy import masked_sample
+
+    def opponent(obs, mask):  # model_greedy_policy_from: argmax of the masked logits (scripts/eval_suite.py:131-141)
+        return masked_sample(net.actor(obs.to(dtype)), mask, greedy=True, want_logprob=False)[0]
 
     for t in range(num_steps):
         x = env.obs.to(dtype)
-        logits = masked_logits(net.actor(x).float(), env.mask)
-        dist = torch.distributions.Categorical(logits=logits)
-        action = dist.sample()
+        # masked categorical sample + log-prob in one kernel (ppo_splendor.py:27-38,54-59)
+        action, logprob, _ = masked_sample(net.actor(x), env.mask, t=env._t)
         buffers["obs"][t].copy_(env.obs)
         buffers["masks"][t].copy_(env.mask)
         buffers["actions"][t].copy_(action)
-        buffers["logprobs"][t].copy_(dist.log_prob(action))
+        buffers["logprobs"][t].copy_(logprob)
         buffers["values"][t].copy_(net.critic(x).float().squeeze(1))
-        _, agent_r, _, _, done, _ = env.dual_step(action.to(torch.int32), opponent)
+        _, agent_r, _, _, done, _ = env.dual_step(action, opponent)
         buffers["rewards"][t].copy_(agent_r)
         buffers["terminals"][t].copy_(done)
     return buffers
@@ -94,6 +97,8 @@ def main(argv=None):
         while done < args.num_steps:
             k = min(chunk, args.num_steps - done)
             collect(env, net, k, buffers=buf, dtype=dtype)
+            if k == chunk:
+                advantages(env, net, buf, dtype=dtype)
             done += k
             steps += k
     e1.record()

@@ -104,3 +104,16 @@ def test_gae_against_reference_formula():
                torch.tensor(last).cuda(), gamma, lam)
     assert np.allclose(a.cpu().numpy(), adv, atol=2e-5, rtol=1e-5)
     assert np.allclose(r.cpu().numpy(), ret, atol=2e-5, rtol=1e-5)
+
+
+def test_batched_eval_vs_opponent():
+    """eval_vs_opponent (scripts/eval_suite.py:162-208), batched: greedy_v1 beats the random opponent, and playing
+    a bot against itself-ish keeps the bookkeeping consistent."""
+    from splendor_gym_b200.policy import scripted_action
+    from splendor_gym_b200.scripts.eval_suite import eval_vs_opponent
+
+    res = eval_vs_opponent(lambda obs, mask: scripted_action(obs, mask, "greedy_v1"), "random", n_games=2000, seed=1)
+    assert res["n"] == 2000 and res["wins"] + res["losses"] + res["draws"] == 2000
+    assert res["win_rate"] > 0.6 and res["illegal_action_rate"] < 0.05 and 5 < res["avg_turns"] <= 100
+    res2 = eval_vs_opponent(lambda obs, mask: scripted_action(obs, mask, "random", t=7), "basic", n_games=1000, seed=2)
+    assert res2["win_rate"] < 0.5
