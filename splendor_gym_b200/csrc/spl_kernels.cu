@@ -18,7 +18,6 @@
 #include "spl_core.cuh"
 #include "spl_tables_host.h"
 
-#define SPL_WARPS_PER_CTA 4
 #define SPL_TILE_WORDS 2376 /* 32 envs * 297 bytes / 4 */
 #define SPL_FULL 0xFFFFFFFFu
 #define SPL_DECK_SMEM 100 /* per-lane deck row in shared memory: 25 words (odd) to spread banks */
@@ -415,7 +414,7 @@ __global__ void __launch_bounds__(WPC * 32) spl_rollout_kernel(const StepParams 
 	const int64_t ntiles = (p.n + 31) >> 5;
 	const uint64_t t0 = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
 
-	// CTA-uniform trip count (tile groups of SPL_WARPS_PER_CTA) so that the optional per-step barrier is safe
+	// CTA-uniform trip count (tile groups of WPC) so that the optional per-step barrier is safe
 	for (int64_t tg = blockIdx.x; tg * WPC < ntiles; tg += gridDim.x) {
 		tl.ti = tg * WPC + warp;
 		const int64_t env = tl.ti * 32 + tl.lane;
@@ -455,8 +454,8 @@ __global__ void __launch_bounds__(WPC * 32) spl_rollout_kernel(const StepParams 
 // ------------------------------------------------------------------------------------------------
 // reset kernel: initial_state (engine/state.py:181-211) for a list of environments.
 // One warp per CTA, one environment per lane; the deck order is built in shared memory.
-//   SPL_SHUFFLE_MT19937: CPython random.Random(seed): init_by_array + shuffle by _randbelow, bit-exact
-//   SPL_SHUFFLE_PHILOX : same Fisher-Yates with a Philox4x32-10 stream keyed by (seed, episode, env)
+//   SPL_SHUFFLE_MT19937: CPython random.Random(seed): init_by_array + shuffle by _randbelow, bit-exact (one env per lane)
+//   SPL_SHUFFLE_PHILOX : the warp-cooperative sort-by-key deal (spl_coop_deal), one env at a time per warp
 // ------------------------------------------------------------------------------------------------
 struct ResetParams {
 	uint4* state;
@@ -519,38 +518,6 @@ struct SplMT {  // MT19937 state of one lane, lane-interleaved in shared memory 
 		uint32_t r = next() >> (32 - k);
 		while (r >= n) r = next() >> (32 - k);
 		return r;
-	}
-};
-
-struct SplPhiloxStream {
-	uint32_t k0, k1, c1, c2, c3, blk;
-	uint4 buf;
-	int have;
-	__device__ __forceinline__ void init(uint64_t seed, uint64_t genv, uint32_t episode) {
-		k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-		c1 = (uint32_t)genv, c2 = (uint32_t)(genv >> 32), c3 = episode;
-		blk = 0, have = 0;
-	}
-	__device__ __forceinline__ uint32_t next() {
-		if (have == 0) {
-			buf = spl_philox(make_uint4(blk++, c1, c2, c3), k0, k1);
-			have = 4;
-		}
-		uint32_t v = have == 4 ? buf.x : (have == 3 ? buf.y : (have == 2 ? buf.z : buf.w));
-		have--;
-		return v;
-	}
-	__device__ __forceinline__ uint32_t randbelow(uint32_t n) {  // Lemire's unbiased bounded integer
-		uint64_t m = (uint64_t)next() * n;
-		uint32_t l = (uint32_t)m;
-		if (l < n) {
-			uint32_t t = (0u - n) % n;
-			while (l < t) {
-				m = (uint64_t)next() * n;
-				l = (uint32_t)m;
-			}
-		}
-		return (uint32_t)(m >> 32);
 	}
 };
 
