@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsplendor_b200.so")
+LIB_PATH = os.environ.get("SPL_LIB") or os.path.join(HERE, "libsplendor_b200.so")
 
 NUM_ACTIONS = 45
 OBS_DIM = 297

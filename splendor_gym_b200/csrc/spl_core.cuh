@@ -404,6 +404,28 @@ SPL_HD void spl_enforce_token_limit(SplState& s, uint32_t tp, uint32_t turn, con
 	}
 }
 
+// The token-return stream (if this move overflows the hand) is indexed by sums that are only known after the
+// action, but in legitimate play bank + both hands = 25 tokens, so the three possible entries (hand 11/12/13) are
+// known from the opponent's hand at the START of the step: prefetch them into L1 so the dependent table load at the
+// end of the move does not wait on L2.  Purely a hint -- states that break the invariant just miss.
+SPL_HD void spl_prefetch_return_stream(const SplState& s, const uint64_t* ret_table) {
+#if defined(__CUDA_ARCH__) && !defined(SPL_NO_PREFETCH)
+	const uint32_t opp = spl_sum6(s.tok[1]);
+	const uint32_t turn = s.turn, tp = s.flags & SPL_FLAG_TO_PLAY;
+	if (turn - 1u < 99u && opp <= 10u && spl_sum6(s.tok[0]) >= 8u) {
+		const uint32_t base = ((turn - 1u) * 2u + tp) * 3u;
+#pragma unroll
+		for (uint32_t h = 0; h < 3; h++) {  // hand 11+h  =>  bank 25 - (11+h) - opp
+			const uint32_t idx = (base + h) * 15u + (14u - h - opp);
+			asm volatile("prefetch.global.L1 [%0];" ::"l"(ret_table + idx));
+		}
+	}
+#else
+	(void)s;
+	(void)ret_table;
+#endif
+}
+
 struct SplStepResult {
 	float reward;
 	uint32_t terminated;
@@ -428,6 +450,7 @@ SPL_HD void spl_env_step_t(SplState& s, int32_t action, const uint8_t* deck, con
 		out.info = SPL_INFO_ERROR | SPL_INFO_TERMINATED;
 		return;
 	}
+	spl_prefetch_return_stream(s, ret_table);
 	const uint32_t avail = spl_colours_ge(s.bank, 1);
 	// any legal move? a non-empty bank always allows a take-3 (:45-58), so the full mask is only
 	// needed when all five colours are exhausted

@@ -20,6 +20,10 @@
 
 #define SPL_TILE_WORDS 2376 /* 32 envs * 297 bytes / 4 */
 #define SPL_FULL 0xFFFFFFFFu
+#ifndef SPL_STORE_UNROLL
+#define SPL_STORE_UNROLL 2
+#endif
+constexpr int kStoreUnroll = SPL_STORE_UNROLL;
 #define SPL_DECK_SMEM 100 /* per-lane deck row in shared memory: 25 words (odd) to spread banks */
 
 __device__ SplTables g_tables;
@@ -120,16 +124,33 @@ struct SplObsStager {
 	__device__ __forceinline__ void last(uint32_t v) { put(74, v | (next_r0 << 8)); }
 };
 
-// stream a staged tile to global memory as int32 (rows == 32: 2376 aligned int4; otherwise per entry)
+// stream a staged tile to global memory as int32.  Full tile: 1188 x (LDS.64 -> 8 byte-extracts -> one 256-bit
+// streaming store), i.e. each lane writes one whole 32-byte sector per instruction and the warp 1 KB; otherwise
+// (ragged last tile / unaligned caller buffer) per entry.
 __device__ __forceinline__ void spl_store_obs_tile(int32_t* gtile, const uint32_t* tile, int lane, int rows, bool vec) {
 	if (rows == 32 && vec) {
-		int4* g4 = reinterpret_cast<int4*>(gtile);
-#pragma unroll 2
-		for (int q = lane; q < SPL_TILE_WORDS; q += 32) {
-			uint32_t v = tile[q];
-			int4 o = make_int4((int)(v & 0xFFu), (int)((v >> 8) & 0xFFu), (int)((v >> 16) & 0xFFu), (int)(v >> 24));
-			__stcs(g4 + q, o);
+#ifndef SPL_STORE128
+		const uint2* t2 = reinterpret_cast<const uint2*>(tile) + lane;
+		int32_t* g = gtile + 8 * lane;
+#pragma unroll kStoreUnroll
+		for (int q = lane; q < SPL_TILE_WORDS / 2; q += 32, t2 += 32, g += 256) {
+			const uint2 v = *t2;
+			asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g), "r"(__byte_perm(v.x, 0, 0x4440)),
+			             "r"(__byte_perm(v.x, 0, 0x4441)), "r"(__byte_perm(v.x, 0, 0x4442)), "r"(__byte_perm(v.x, 0, 0x4443)),
+			             "r"(__byte_perm(v.y, 0, 0x4440)), "r"(__byte_perm(v.y, 0, 0x4441)), "r"(__byte_perm(v.y, 0, 0x4442)),
+			             "r"(__byte_perm(v.y, 0, 0x4443))
+			             : "memory");
 		}
+#else
+		const uint32_t* t1 = tile + lane;
+		int4* g4 = reinterpret_cast<int4*>(gtile) + lane;
+#pragma unroll kStoreUnroll
+		for (int q = lane; q < SPL_TILE_WORDS; q += 32, t1 += 32, g4 += 32) {
+			const uint32_t v = *t1;
+			__stcs(g4, make_int4((int)__byte_perm(v, 0, 0x4440), (int)__byte_perm(v, 0, 0x4441), (int)__byte_perm(v, 0, 0x4442),
+			                     (int)__byte_perm(v, 0, 0x4443)));
+		}
+#endif
 	} else {
 		const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
 		for (int e = lane; e < rows * SPL_OBS_DIM; e += 32) gtile[e] = (int32_t)tb[e];
@@ -140,8 +161,8 @@ __device__ __forceinline__ void spl_store_obs_tile(int32_t* gtile, const uint32_
 // Native (Philox) deal: a uniformly random permutation of each deck and of the nobles by SORTING
 // RANDOM KEYS, done by the whole warp for ONE environment (the rest of the warp would otherwise idle
 // while a single lane ran a 100-step Fisher-Yates).  Element e (cards 0..89, nobles 90..99) gets the key
-// philox4x32-10(ctr = {e/4, env_lo, env_hi, episode}, key = seed)[e%4]; its position in its deck is the
-// rank of (key, e) among the elements of the same tier.  The deal is a pure function of
+// philox4x32-10(ctr = {e/4, env_lo, env_hi, episode}, key = seed)[e%4] with its low 7 bits replaced by e; its
+// position in its deck is the rank of that key among the elements of the same tier.  The deal is a pure function of
 // (seed, global env id, episode), so it does not depend on the GPU count or on which kernel performs it.
 // `scratch` = >= 132 words of shared memory private to the warp.  Writes the 96-byte deck row to `gdeck`.
 // ------------------------------------------------------------------------------------------------
@@ -153,6 +174,10 @@ __device__ __forceinline__ void spl_coop_deal(uint64_t seed, uint64_t genv, uint
 	if (lane < 25) {
 		uint4 c = spl_philox(make_uint4((uint32_t)lane, (uint32_t)genv, (uint32_t)(genv >> 32), episode), (uint32_t)seed,
 		                     (uint32_t)(seed >> 32));
+		// low 7 bits <- element index: keys become unique, so a rank is a plain count of smaller keys
+		// (25 random bits decide the order; the index only breaks the ~1e-4-probable ties)
+		const uint32_t e = 4u * (uint32_t)lane;
+		c.x = (c.x & ~127u) | e, c.y = (c.y & ~127u) | (e + 1), c.z = (c.z & ~127u) | (e + 2), c.w = (c.w & ~127u) | (e + 3);
 		*reinterpret_cast<uint4*>(keys + 4 * lane) = c;
 	}
 	if (lane < 24) reinterpret_cast<uint32_t*>(sdeck)[lane] = 0xFFFFFFFFu;
@@ -164,8 +189,8 @@ __device__ __forceinline__ void spl_coop_deal(uint64_t seed, uint64_t genv, uint
 #pragma unroll 4
 		for (uint32_t i = 0; i < 40; i++) {
 			uint32_t ki = keys[i];
-			r0 += (ki < k0) || (ki == k0 && i < e0);
-			r1 += (ki < k1) || (ki == k1 && i < e1);
+			r0 += ki < k0;
+			r1 += ki < k1;
 		}
 		sdeck[r0] = (uint8_t)e0;
 		if (lane < 8) sdeck[r1] = (uint8_t)e1;
@@ -177,17 +202,17 @@ __device__ __forceinline__ void spl_coop_deal(uint64_t seed, uint64_t genv, uint
 #pragma unroll 2
 		for (uint32_t i = 40; i < 70; i++) {
 			uint32_t ki = keys[i];
-			r2 += (ki < k2) || (ki == k2 && i < e2);
+			r2 += ki < k2;
 		}
 #pragma unroll 2
 		for (uint32_t i = 70; i < 90; i++) {
 			uint32_t ki = keys[i];
-			r3 += (ki < k3) || (ki == k3 && i < e3);
+			r3 += ki < k3;
 		}
 #pragma unroll 2
 		for (uint32_t i = 90; i < 100; i++) {
 			uint32_t ki = keys[i];
-			r4 += (ki < k4) || (ki == k4 && i < e4);
+			r4 += ki < k4;
 		}
 		if (lane < 30) sdeck[40 + r2] = (uint8_t)e2;
 		if (lane < 20) sdeck[70 + r3] = (uint8_t)e3;
@@ -238,7 +263,7 @@ struct StepParams {
 	uint64_t action_key, action_t;
 	const uint64_t* action_t_base;
 	int reset_mode;
-	int vec_ok;  // obs / mask bases are 16-byte aligned
+	int vec_ok;  // obs / mask bases are 32-byte aligned (and, for step-major buffers, every step's slice is)
 	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
 	int sync;    // rollout kernel: CTA barrier per lock-step (keeps the warps of a CTA in the same code region)
 };
@@ -892,7 +917,7 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.action_t_base = io ? io->action_t_base : nullptr;
 	p.reset_mode = SPL_RESET_NONE;
 	if (io && io->autoreset) p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED : SPL_RESET_WORKLIST;
-	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;
+	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 31) == 0;  // 256-bit observation stores, 128-bit mask stores
 	p.steps = 1;
 	p.sync = 0;
 }
