@@ -20,10 +20,6 @@
 
 #define SPL_TILE_WORDS 2376 /* 32 envs * 297 bytes / 4 */
 #define SPL_FULL 0xFFFFFFFFu
-#ifndef SPL_STORE_UNROLL
-#define SPL_STORE_UNROLL 2
-#endif
-constexpr int kStoreUnroll = SPL_STORE_UNROLL;
 #define SPL_DECK_SMEM 100 /* per-lane deck row in shared memory: 25 words (odd) to spread banks */
 
 __device__ SplTables g_tables;
@@ -124,33 +120,19 @@ struct SplObsStager {
 	__device__ __forceinline__ void last(uint32_t v) { put(74, v | (next_r0 << 8)); }
 };
 
-// stream a staged tile to global memory as int32.  Full tile: 1188 x (LDS.64 -> 8 byte-extracts -> one 256-bit
-// streaming store), i.e. each lane writes one whole 32-byte sector per instruction and the warp 1 KB; otherwise
-// (ragged last tile / unaligned caller buffer) per entry.
+// stream a staged tile to global memory as int32.  Full tile: 2376 x (LDS.32 -> 4 PRMT byte-extracts -> STG.128
+// streaming store), the warp writing 512 contiguous bytes per instruction; otherwise (ragged last tile / unaligned
+// caller buffer) per entry.  (256-bit stores, st.global.v8.b32 = STG.256 on sm_100a, were measured 8 % SLOWER here.)
 __device__ __forceinline__ void spl_store_obs_tile(int32_t* gtile, const uint32_t* tile, int lane, int rows, bool vec) {
 	if (rows == 32 && vec) {
-#ifndef SPL_STORE128
-		const uint2* t2 = reinterpret_cast<const uint2*>(tile) + lane;
-		int32_t* g = gtile + 8 * lane;
-#pragma unroll kStoreUnroll
-		for (int q = lane; q < SPL_TILE_WORDS / 2; q += 32, t2 += 32, g += 256) {
-			const uint2 v = *t2;
-			asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g), "r"(__byte_perm(v.x, 0, 0x4440)),
-			             "r"(__byte_perm(v.x, 0, 0x4441)), "r"(__byte_perm(v.x, 0, 0x4442)), "r"(__byte_perm(v.x, 0, 0x4443)),
-			             "r"(__byte_perm(v.y, 0, 0x4440)), "r"(__byte_perm(v.y, 0, 0x4441)), "r"(__byte_perm(v.y, 0, 0x4442)),
-			             "r"(__byte_perm(v.y, 0, 0x4443))
-			             : "memory");
-		}
-#else
 		const uint32_t* t1 = tile + lane;
 		int4* g4 = reinterpret_cast<int4*>(gtile) + lane;
-#pragma unroll kStoreUnroll
+#pragma unroll 2
 		for (int q = lane; q < SPL_TILE_WORDS; q += 32, t1 += 32, g4 += 32) {
 			const uint32_t v = *t1;
 			__stcs(g4, make_int4((int)__byte_perm(v, 0, 0x4440), (int)__byte_perm(v, 0, 0x4441), (int)__byte_perm(v, 0, 0x4442),
 			                     (int)__byte_perm(v, 0, 0x4443)));
 		}
-#endif
 	} else {
 		const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
 		for (int e = lane; e < rows * SPL_OBS_DIM; e += 32) gtile[e] = (int32_t)tb[e];
@@ -263,7 +245,7 @@ struct StepParams {
 	uint64_t action_key, action_t;
 	const uint64_t* action_t_base;
 	int reset_mode;
-	int vec_ok;  // obs / mask bases are 32-byte aligned (and, for step-major buffers, every step's slice is)
+	int vec_ok;  // obs / mask bases are 16-byte aligned (and, for step-major buffers, every step's slice is)
 	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
 	int sync;    // rollout kernel: CTA barrier per lock-step (keeps the warps of a CTA in the same code region)
 };
@@ -917,7 +899,7 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.action_t_base = io ? io->action_t_base : nullptr;
 	p.reset_mode = SPL_RESET_NONE;
 	if (io && io->autoreset) p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED : SPL_RESET_WORKLIST;
-	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 31) == 0;  // 256-bit observation stores, 128-bit mask stores
+	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;  // 128-bit tile stores
 	p.steps = 1;
 	p.sync = 0;
 }
