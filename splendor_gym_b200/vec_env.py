@@ -20,6 +20,37 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+class _LazyInfo(dict):
+    _DERIVED = {
+        "illegal_action": lambda b: (b & L.INFO_ILLEGAL) != 0,
+        "draw": lambda b: (b & L.INFO_NOLEGAL_DRAW) != 0,
+        "turn_limit": lambda b: (b & L.INFO_TURN_LIMIT) != 0,
+        "winner": lambda b: ((b & L.INFO_WINNER_MASK) >> L.INFO_WINNER_SHIFT).to(torch.int8) - 1,
+        "error": lambda b: (b & L.INFO_ERROR) != 0,
+        "reset": lambda b: (b & L.INFO_RESET) != 0,
+    }
+
+    def __init__(self, mask, to_play, bits):
+        super().__init__(action_mask=mask, to_play=to_play, info_bits=bits)
+
+    def __missing__(self, key):
+        fn = self._DERIVED.get(key)
+        if fn is None:
+            raise KeyError(key)
+        val = fn(self["info_bits"])
+        self[key] = val
+        return val
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._DERIVED
+
+
 class SplendorVecEnv:
     """Batched ``SplendorEnv`` (splendor_gym/envs/splendor_env.py:23-130).
 
@@ -86,19 +117,10 @@ class SplendorVecEnv:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def info(self) -> Dict[str, torch.Tensor]:
-        """The reference's info dict, batched (envs/splendor_env.py:47-48,82-88)."""
-        b = self.info_bits
-        return {
-            "action_mask": self.mask,
-            "to_play": self.obs[:, 294],
-            "illegal_action": (b & L.INFO_ILLEGAL) != 0,
-            "draw": (b & L.INFO_NOLEGAL_DRAW) != 0,
-            "turn_limit": (b & L.INFO_TURN_LIMIT) != 0,
-            "winner": ((b & L.INFO_WINNER_MASK) >> L.INFO_WINNER_SHIFT).to(torch.int8) - 1,
-            "error": (b & L.INFO_ERROR) != 0,
-            "reset": (b & L.INFO_RESET) != 0,
-            "info_bits": b,
-        }
+        """The reference's info dict, batched (envs/splendor_env.py:47-48,82-88).  "action_mask", "to_play" and
+        "info_bits" are views of the step outputs; the boolean / winner entries are decoded from the info bits on
+        first access (no extra kernels on the step path unless somebody asks)."""
+        return _LazyInfo(self.mask, self.obs[:, 294], self.info_bits)
 
     @staticmethod
     def final_rewards(info_bits: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
