@@ -18,6 +18,8 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
 iA, iS, iW, iE = hdr.index("Address"), hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
+KINDS = ["stall_long_sb", "stall_short_sb", "stall_wait", "stall_barrier", "stall_mio", "stall_lg", "stall_math", "stall_no_inst", "stall_branch_resolving"]
+iK = [hdr.index(k) for k in KINDS]
 prof, last = [], -1
 for r in rows[2:]:
     if len(r) <= iE or not r[iA].startswith("0x"):
@@ -26,7 +28,7 @@ for r in rows[2:]:
     if a < last:
         break
     last = a
-    prof.append((r[iS].strip(), int(r[iW] or 0), int(r[iE] or 0)))
+    prof.append((r[iS].strip(), int(r[iW] or 0), int(r[iE] or 0), [int(r[i] or 0) for i in iK]))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "splendor_gym_b200", "libsplendor_b200.so")], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.startswith("spl_kernels.") and f.endswith(".cubin")][0]
@@ -59,12 +61,16 @@ def owner(fn, ln):
 
 
 stall, execd = collections.Counter(), collections.Counter()
+kinds = collections.defaultdict(lambda: [0] * len(KINDS))
 for i in range(n):
     o = owner(*lines[i][0]) if lines[i][0] else "?"
     stall[o] += prof[i][1]
     execd[o] += prof[i][2]
+    for j, v in enumerate(prof[i][3]):
+        kinds[o][j] += v
 ts, te = sum(stall.values()), sum(execd.values())
-print(f"{'function':34s} {'stall%':>7s} {'exec%':>7s} {'exec per warp-step':>18s}")
-for k, v in stall.most_common(30):
-    print(f"{k:34s} {100*v/ts:7.1f} {100*execd[k]/te:7.1f} {execd[k]/denom:18.1f}")
-print(f"{'total':34s} {100.0:7.1f} {100.0:7.1f} {te/denom:18.1f}")
+print(f"{'function':30s} {'stall%':>7s} {'exec%':>7s} {'exec/warp-step':>14s}  " + " ".join(f"{k[6:10]:>5s}" for k in KINDS) + "   (stall kinds in % of all samples)")
+for k, v in stall.most_common(24):
+    print(f"{k:30s} {100*v/ts:7.1f} {100*execd[k]/te:7.1f} {execd[k]/denom:14.1f}  " + " ".join(f"{100*x/ts:5.1f}" for x in kinds[k]))
+tot = [sum(kinds[k][j] for k in kinds) for j in range(len(KINDS))]
+print(f"{'all':30s} {100.0:7.1f} {100.0:7.1f} {te/denom:14.1f}  " + " ".join(f"{100*x/ts:5.1f}" for x in tot))
