@@ -386,3 +386,40 @@ def test_fused_reset_equals_reset_kernel(VecEnv):
         actions = a.next_action.clone()
     assert resets > 1000
     assert torch.equal(a.export_state(), b.export_state()) and torch.equal(a.episode, b.episode)
+
+
+def test_unaligned_output_buffers_and_strided_state(VecEnv, oracle):
+    """The C ABI accepts caller buffers that are not 16-byte aligned (scalar store path) and a state stride larger
+    than n (a shard that is a prefix of a bigger allocation); results are unchanged."""
+    import ctypes as C
+
+    from splendor_gym_b200 import _lib as L
+
+    n, cap = 200, 256
+    env = VecEnv(cap, seed=3, shuffle="mt19937", autoreset=True)
+    # shrink the logical shard to the first n envs of the cap-sized planes
+    env._envs.n = n
+    env.n = n
+    ref = oracle.OracleVec(n, seed_base=3)
+    big_obs = torch.zeros(cap * 297 + 8, dtype=torch.int32, device="cuda")
+    big_mask = torch.zeros(cap * 45 + 8, dtype=torch.int8, device="cuda")
+    obs = big_obs[1:1 + n * 297].view(n, 297)      # 4-byte offset: not 16-byte aligned
+    mask = big_mask[3:3 + n * 45].view(n, 45)      # 3-byte offset
+    assert obs.data_ptr() % 16 != 0 and mask.data_ptr() % 16 != 0
+    lib = L.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    L.check(lib.spl_reset(C.byref(env._envs), None, None, obs.data_ptr(), mask.data_ptr(), stream))
+    robs, rmask = ref.reset()
+    assert np.array_equal(_np(obs), robs) and np.array_equal(_np(mask), rmask)
+    env._is_reset = True
+    for t in range(150):
+        a = ref.random_actions(7, t)
+        out = env.step(torch.from_numpy(a).cuda(), out_obs=obs, out_mask=mask)
+        robs, rrew, rterm, rinfo, rmask = ref.step(a, autoreset=True)
+        assert np.array_equal(_np(obs), robs), f"step {t}"
+        assert np.array_equal(_np(mask), rmask), f"step {t}"
+        assert np.array_equal(_np(env.reward)[:n], rrew) and np.array_equal(_np(env._terminated)[:n], rterm)
+    assert int(big_obs[0]) == 0 and int(big_obs[1 + n * 297:].abs().sum()) == 0  # nothing written outside the view
+    assert int(big_mask[:3].abs().sum()) == 0 and int(big_mask[3 + n * 45:].abs().sum()) == 0
+    rows = _np(env.export_state())[:n]
+    assert np.array_equal(rows, ref.export_rows())
