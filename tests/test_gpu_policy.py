@@ -117,3 +117,14 @@ def test_batched_eval_vs_opponent():
     assert res["win_rate"] > 0.6 and res["illegal_action_rate"] < 0.05 and 5 < res["avg_turns"] <= 100
     res2 = eval_vs_opponent(lambda obs, mask: scripted_action(obs, mask, "random", t=7), "basic", n_games=1000, seed=2)
     assert res2["win_rate"] < 0.5
+
+
+def test_ppo_training_smoke():
+    """The end-to-end trainer (device rollout + PPO update of ppo_splendor.py:327-361) runs, fills the pool, evaluates."""
+    from splendor_gym_b200.scripts import ppo_train
+
+    log = ppo_train.main(["--num-envs", "512", "--num-steps", "32", "--total-timesteps", str(512 * 32 * 4), "--minibatch-size", "4096",
+                          "--snapshot-every-updates", "1", "--eval-every-updates", "4", "--eval-games", "256", "--update-epochs", "2"])
+    assert len(log) == 4 and all(r["rollout_agent_steps_per_s"] > 0 for r in log)
+    assert "win_rate_vs_random" in log[-1] and 0.0 <= log[-1]["win_rate_vs_random"] <= 1.0
+    assert log[-1]["episodes"] > 0
