@@ -166,7 +166,7 @@ def main(argv=None):
                 loss.backward()
                 nn.utils.clip_grad_norm_(net.parameters(), 0.5)
                 opt.step()
-                if args.target_kl > 0 and float((b_logp[idx] - new_logp).mean()) > args.target_kl:
+                if args.target_kl > 0 and float((b_logp[idx] - new_logp.detach()).mean()) > args.target_kl:
                     stop = True
                     break
             if stop:

@@ -35,22 +35,24 @@ def main(argv=None):
 
     from ..envs import SplendorEnv
 
-    env = SplendorEnv(num_players=2)
-    wins = 0
-    reward = 0.0
-    for ep in range(args.episodes):
-        obs, info = env.reset(seed=args.seed + ep)
-        done, steps = False, 0
-        while not done and steps < 500:
-            mask = info["action_mask"]
-            if mask.sum() == 0:
+    def play_one(env, seed: int, cap: int = 500):
+        """One game of uniformly random legal moves on the facade; returns (moves, last reward)."""
+        _, info = env.reset(seed=seed)
+        last, moves = 0.0, 0
+        for moves in range(1, cap + 1):
+            legal = np.flatnonzero(info["action_mask"])
+            if legal.size == 0:
+                return moves - 1, last
+            _, last, terminated, truncated, info = env.step(int(np.random.choice(legal)))
+            if terminated or truncated:
                 break
-            action = int(np.random.choice(np.flatnonzero(mask)))
-            obs, reward, terminated, truncated, info = env.step(action)
-            steps += 1
-            done = terminated or truncated
+        return moves, last
+
+    env = SplendorEnv(num_players=2)
+    outcomes = [play_one(env, args.seed + ep) for ep in range(args.episodes)]
+    for ep, (steps, reward) in enumerate(outcomes):
         print(f"Episode {ep}: steps={steps} reward={reward}")
-        wins += reward > 0
+    wins = sum(1 for _, r in outcomes if r > 0)
     print(f"Wins: {wins}/{args.episodes}")
     return wins
 
