@@ -128,3 +128,32 @@ def test_ppo_training_smoke():
     assert len(log) == 4 and all(r["rollout_agent_steps_per_s"] > 0 for r in log)
     assert "win_rate_vs_random" in log[-1] and 0.0 <= log[-1]["win_rate_vs_random"] <= 1.0
     assert log[-1]["episodes"] > 0
+
+
+def test_trajectory_log_and_replay():
+    """4 bytes per env-step (+ the start state) regenerate the whole rollout: replaying the action log reproduces the
+    rewards / terminations / final state of the recorded run and every observation of a directly recorded run."""
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200.trajectory import Trajectory, describe_action, record_random, replay
+
+    n, T = 2048, 160
+    env = SplendorVecEnv(n, seed=21, shuffle="philox", autoreset=True)
+    env.reset()
+    for _ in range(10):  # start the log mid-game
+        env.step(env.sample_random_actions())
+    # reference run that keeps observations
+    twin = SplendorVecEnv(n, seed=21, shuffle="philox", autoreset=True)
+    twin.reset()
+    for _ in range(10):
+        twin.step(twin.sample_random_actions())
+    traj = record_random(env, T, seed=21)
+    assert traj.bytes_per_env_step < 5.5
+    env2, rew, term, obs = replay(traj, keep_obs=True)
+    assert torch.equal(rew, traj.rewards) and torch.equal(term, traj.terminated)
+    assert torch.equal(env2.export_state(), env.export_state())
+    for t in range(T):
+        o, *_ = twin.step(traj.actions[t])
+        assert torch.equal(o, obs[t]), t
+    assert int(traj.terminated.sum()) > 1000
+    assert describe_action(0) == "Take3: WUG" and describe_action(12) == "Take2: GG" and describe_action(20) == "Buy: T2S2"
+    assert describe_action(41) == "Reserve: T3 deck" and describe_action(0, bank=[1, 0, 2, 0, 0, 0]) == "Take2: WG (reduced)"
