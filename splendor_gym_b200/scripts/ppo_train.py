@@ -175,7 +175,7 @@ def main(argv=None):
             pool.add_snapshot()
         torch.cuda.synchronize()
         rec = {"update": update + 1, "global_step": global_step, "rollout_agent_steps_per_s": n * T / t_roll,
-               "update_s": time.perf_counter() - t0 - t_roll, "episodes": int(env.stats[0]), "loss": float(loss)}
+               "update_s": time.perf_counter() - t0 - t_roll, "episodes": int(env.stats[0]), "loss": float(loss.detach())}
         if (update + 1) % max(1, args.eval_every_updates) == 0 or update + 1 == num_updates:
             @torch.no_grad()
             def greedy(obs, mask):
