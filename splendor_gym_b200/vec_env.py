@@ -106,11 +106,25 @@ class SplendorVecEnv:
             scratch=self.scratch.data_ptr(), stride=n, n=n, env_offset=int(env_offset), seed_base=int(seed),
             shuffle_mode=self.shuffle_mode, reserved_=0,
         )
+        # gymnasium.vector-style attributes (what gym.vector.SyncVectorEnv exposes, ppo_splendor.py:151-159)
+        from .envs._gym_compat import spaces
+        import numpy as _np
+
+        self.num_envs = n
+        self.single_action_space = spaces.Discrete(L.NUM_ACTIONS)
+        self.single_observation_space = spaces.Box(low=0, high=50, shape=(L.OBS_DIM,), dtype=_np.int32)
         self._io = L.SplStepIO()
         self._t = 0  # lock-step counter (drives the Philox action stream)
         self.t_base = None  # optional device int64 scalar added to the counter (CUDA-graph replays)
         self.action_key = 0xB200
         self._is_reset = False
+
+    def close(self) -> None:
+        """Nothing to release beyond the tensors (kept for gymnasium.vector API parity)."""
+
+    def episode_statistics(self) -> Dict[str, int]:
+        """Counters accumulated by the step kernels since construction (one host read)."""
+        return dict(zip(L.STAT_NAMES, self.stats.cpu().tolist()))
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self) -> int:
