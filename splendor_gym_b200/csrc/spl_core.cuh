@@ -438,9 +438,32 @@ struct SplStepResult {
 // ------------------------------------------------------------------------------------------------
 // KNOWN_MASK: the caller already holds legal_moves(state) as a bit set (`cur_mask`) -- the reference computes
 // exactly that at the top of step() (:55) -- otherwise legality is evaluated for the one action only.
+SPL_HD uint32_t spl_deck_byte(const uint8_t* deck, uint32_t idx) {
+#if defined(__CUDA_ARCH__)
+	return __ldcg(deck + idx);  // L2-coherent: the row may have been written by other lanes (fused reset)
+#else
+	return deck[idx];
+#endif
+}
+
+// top card of each deck (bytes 0..2; 0xFF when the deck is empty) -- see `tops` below
+SPL_HD uint32_t spl_deck_tops(const SplState& s, const uint8_t* deck) {
+	uint32_t tops = 0xFFFFFFu;
+	const uint32_t off[3] = {0u, 40u, 70u};
+#pragma unroll
+	for (int t = 0; t < 3; t++) {
+		uint32_t dn = (s.deckn >> (8 * t)) & 0xFFu;
+		if (dn > 0) tops = (tops & ~(0xFFu << (8 * t))) | (spl_deck_byte(deck, off[t] + dn - 1) << (8 * t));
+	}
+	return tops;
+}
+
+// KNOWN_MASK: see above.  `tops` (nullable): the caller keeps the top card of each deck in a register across
+// steps; a pop then takes the card from the register and issues the load of the NEW top, which nobody waits for
+// until that deck is popped again -- the dependent global load leaves the critical path of the step.
 template <bool KNOWN_MASK>
 SPL_HD void spl_env_step_t(SplState& s, int32_t action, const uint8_t* deck, const SplTables* T, const uint64_t* ret_table,
-                           SplStepResult& out, uint64_t cur_mask) {
+                           SplStepResult& out, uint64_t cur_mask, uint32_t* tops = nullptr) {
 	out.reward = 0.0f;
 	out.terminated = 0;
 	out.info = 0;
@@ -516,11 +539,14 @@ SPL_HD void spl_env_step_t(SplState& s, int32_t action, const uint8_t* deck, con
 		uint32_t dn = (s.deckn >> (8 * pop_tier)) & 0xFFu;
 		if (dn > 0) {
 			uint32_t off = pop_tier == 0 ? 0u : (pop_tier == 1 ? 40u : 70u);
-#if defined(__CUDA_ARCH__)
-			popped = __ldcg(deck + off + dn - 1);  // L2-coherent: the row may have been written by other lanes (fused reset)
-#else
-			popped = deck[off + dn - 1];
-#endif
+			if (tops != nullptr) {
+				const uint32_t sh = 8u * (uint32_t)pop_tier;
+				popped = (*tops >> sh) & 0xFFu;
+				const uint32_t next = dn > 1 ? spl_deck_byte(deck, off + dn - 2) : SPL_EMPTY;
+				*tops = (*tops & ~(0xFFu << sh)) | (next << sh);
+			} else {
+				popped = spl_deck_byte(deck, off + dn - 1);
+			}
 			s.deckn -= 1u << (8 * pop_tier);
 		}
 	}

@@ -149,7 +149,7 @@ __device__ __forceinline__ void spl_store_obs_tile(int32_t* gtile, const uint32_
 // `scratch` = >= 132 words of shared memory private to the warp.  Writes the 96-byte deck row to `gdeck`.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void spl_coop_deal(uint64_t seed, uint64_t genv, uint32_t episode, uint32_t* scratch, int lane,
-                                              uint8_t* gdeck, uint32_t board[3], uint32_t& nobles) {
+                                              uint8_t* gdeck, uint32_t board[3], uint32_t& nobles, uint32_t& tops) {
 	uint32_t* keys = scratch;                                      // [100] (+4 pad)
 	uint8_t* sdeck = reinterpret_cast<uint8_t*>(scratch + 104);    // [96]
 	uint8_t* snob = reinterpret_cast<uint8_t*>(scratch + 128);     // [10] (+pad)
@@ -207,6 +207,7 @@ __device__ __forceinline__ void spl_coop_deal(uint64_t seed, uint64_t genv, uint
 	board[1] = __byte_perm(d32[16], d32[17], 0x2345);                   // deck2 = bytes 40..69: [69],[68],[67],[66]
 	board[2] = __byte_perm(d32[21], d32[22], 0x2345);                   // deck3 = bytes 70..89: [89],[88],[87],[86]
 	nobles = (uint32_t)snob[0] | ((uint32_t)snob[1] << 8) | ((uint32_t)snob[2] << 16);
+	tops = (uint32_t)sdeck[35] | ((uint32_t)sdeck[40 + 25] << 8) | ((uint32_t)sdeck[70 + 15] << 16);  // tops after dealing 4
 	if (lane < 24) reinterpret_cast<uint32_t*>(gdeck)[lane] = d32[lane];
 	__syncwarp();
 }
@@ -261,10 +262,10 @@ struct SplTile {
 // one SplendorEnv.step for the lane's env + episode statistics + same-step auto-reset
 template <bool KNOWN_MASK>
 __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile& tl, SplState& s, bool act, int32_t action, int64_t env,
-                                              SplStepResult& r, uint64_t cur_mask = 0) {
+                                              SplStepResult& r, uint64_t cur_mask = 0, uint32_t* tops = nullptr) {
 	const int lane = tl.lane;
 	r.reward = 0.0f, r.terminated = 0, r.info = 0;
-	if (act) spl_env_step_t<KNOWN_MASK>(s, action, p.decks + env * SPL_DECK_STRIDE, tl.T, g_ret_table, r, cur_mask);
+	if (act) spl_env_step_t<KNOWN_MASK>(s, action, p.decks + env * SPL_DECK_STRIDE, tl.T, g_ret_table, r, cur_mask, tops);
 	const bool finished = r.terminated && !(r.info & SPL_INFO_ERROR);
 	const bool do_reset = act && r.terminated && p.reset_mode != SPL_RESET_NONE;
 	if (do_reset) r.info |= SPL_INFO_RESET;
@@ -306,9 +307,12 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 			}
 			ep = __shfl_sync(SPL_FULL, ep, src);
 			const int64_t e = __shfl_sync(SPL_FULL, env, src);
-			uint32_t board[3], nobles;
-			spl_coop_deal(p.seed_base, p.env_offset + (uint64_t)e, ep, tl.smem, lane, p.decks + e * SPL_DECK_STRIDE, board, nobles);
-			if (lane == src) spl_state_from_deal(s, board, nobles);
+			uint32_t board[3], nobles, new_tops;
+			spl_coop_deal(p.seed_base, p.env_offset + (uint64_t)e, ep, tl.smem, lane, p.decks + e * SPL_DECK_STRIDE, board, nobles, new_tops);
+			if (lane == src) {
+				spl_state_from_deal(s, board, nobles);
+				if (tops != nullptr) *tops = new_tops;
+			}
 		}
 	}
 }
@@ -432,6 +436,7 @@ __global__ void __launch_bounds__(WPC * 32) spl_rollout_kernel(const StepParams 
 		SplState s;
 		spl_unpack(w, s);
 		int32_t action = valid ? p.actions[env] : 0;
+		uint32_t tops = valid ? spl_deck_tops(s, p.decks + env * SPL_DECK_STRIDE) : 0xFFFFFFu;
 		// rotated loop: [legal mask of the current state] -> [emit the outputs of the previous step] -> [step].
 		// The mask is needed twice -- as the action mask returned by step t-1 and as the legality check of
 		// step t (envs/splendor_env.py:55,64,81) -- and is computed once; one code copy keeps the hot loop small.
@@ -446,7 +451,7 @@ __global__ void __launch_bounds__(WPC * 32) spl_rollout_kernel(const StepParams 
 			if (st == p.steps) break;
 			const int64_t o = (int64_t)st * p.n;
 			SplStepResult r;
-			spl_tile_step<true>(p, tl, s, valid, action, env, r, m);
+			spl_tile_step<true>(p, tl, s, valid, action, env, r, m, &tops);
 			spl_pack(s, w);
 			if (valid) {
 				p.reward[o + env] = r.reward;
@@ -609,8 +614,8 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 				const int64_t e = __shfl_sync(SPL_FULL, env, src);
 				const uint32_t epr = __shfl_sync(SPL_FULL, ep, src);
 				const uint64_t key = p.seeds ? __shfl_sync(SPL_FULL, seed, src) : p.seed_base;
-				uint32_t board[3], nobles;
-				spl_coop_deal(key, p.env_offset + (uint64_t)e, epr, tile, lane, p.decks + e * SPL_DECK_STRIDE, board, nobles);
+				uint32_t board[3], nobles, tops_unused;
+				spl_coop_deal(key, p.env_offset + (uint64_t)e, epr, tile, lane, p.decks + e * SPL_DECK_STRIDE, board, nobles, tops_unused);
 				if (lane == src) spl_state_from_deal(s, board, nobles);
 			}
 		}
