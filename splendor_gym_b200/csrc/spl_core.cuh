@@ -841,3 +841,43 @@ SPL_HD void spl_import_row(const int32_t* row, SplState& s, uint8_t* deck) {
 	}
 	for (int k = 90; k < SPL_DECK_STRIDE; k++) deck[k] = (uint8_t)SPL_EMPTY;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Rollout work units: how `steps` lock-steps are cut into chunks (see the work-queue comment in spl_kernels.cu)
+// ------------------------------------------------------------------------------------------------
+struct SplChunking {
+	int full, tail_steps;  // `full` chunks of `chunk` steps, then tail_steps split by halving
+};
+
+SPL_HD SplChunking spl_chunking(int steps, int chunk) {
+	SplChunking k;
+	k.full = steps >= 2 * chunk ? (steps - chunk) / chunk : 0;
+	k.tail_steps = steps - k.full * chunk;
+	return k;
+}
+
+// chunk index -> [start, start+len) in lock-steps; returns false past the last chunk
+SPL_HD bool spl_chunk_bounds(int c, int steps, int chunk, int& start, int& len) {
+	const SplChunking k = spl_chunking(steps, chunk);
+	if (c < k.full) {
+		start = c * chunk, len = chunk;
+		return true;
+	}
+	int rem = k.tail_steps, s0 = k.full * chunk;
+	for (int j = k.full;; j++) {
+		if (rem <= 0) return false;
+		const int l = rem > 3 ? rem / 2 : rem;
+		if (j == c) {
+			start = s0, len = l;
+			return true;
+		}
+		s0 += l, rem -= l;
+	}
+}
+
+SPL_HD int spl_num_chunks(int steps, int chunk) {
+	int c = 0, a, b;
+	while (spl_chunk_bounds(c, steps, chunk, a, b)) c++;
+	return c;
+}
+

@@ -249,6 +249,7 @@ struct StepParams {
 	int vec_ok;  // obs / mask bases are 16-byte aligned (and, for step-major buffers, every step's slice is)
 	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
 	int sync;    // rollout kernel: CTA barrier per lock-step (keeps the warps of a CTA in the same code region)
+	int chunk, nchunks;  // rollout kernel: lock-steps per work unit, chunks per tile group (spl_chunk_bounds)
 };
 
 struct SplTile {
@@ -302,7 +303,7 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 			rb &= rb - 1;
 			uint32_t ep = 0;
 			if (lane == src) {
-				ep = p.episode[env] + 1u;
+				ep = __ldcg(p.episode + env) + 1u;  // L2: the previous chunk of this game may have run on another SM
 				p.episode[env] = ep;
 			}
 			ep = __shfl_sync(SPL_FULL, ep, src);
@@ -410,45 +411,97 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 	}
 }
 
-// `steps` lock-steps of uniform-random-legal play with same-step auto-reset in ONE launch: every warp keeps its
-// 32 games in registers and streams each step's observation / mask / reward / terminated / action into
-// [steps][n][...] rollout buffers.  Bit-identical to `steps` calls of spl_step chained through next_action.
+// ------------------------------------------------------------------------------------------------
+// Rollout work queue.  SM store bandwidth on B200 is NOT uniform: a store-only microbenchmark
+// (tools/microbench/store_bw.cu) hands 8 SMs ~2,200 tiles, ~108 SMs ~1,850 and 32 SMs ~1,430 when tiles are
+// taken from an atomic counter, and reaches 7.3-7.5 TB/s that way against 6.0-6.4 TB/s for any static split
+// (the slow SMs finish last, the fast ones idle for 30 % of the run).  The rollout kernel therefore cuts the
+// job into work units (tile group g, chunk c of lock-steps), numbers them chunk-major (u = c*G + g, so the
+// write front still moves linearly through the step-major rollout buffers) and lets persistent CTAs pull
+// units from an atomic counter.  A group's packed state travels between chunks through HBM (128 B per env per
+// chunk); unit (g, c) waits until `done[g]` says chunk c-1 of the same group has been published.  Units are
+// handed out in increasing order and a unit only depends on a smaller one, so the oldest unit in flight never
+// waits: no deadlock as long as units are only held by resident CTAs (they are: a CTA takes one when it runs).
+// Chunk lengths: `chunk` lock-steps each, then the last chunk..2*chunk steps are halved down to 2 so that the
+// tail of the launch (CTAs finding the queue empty) is short.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spl_ld_acquire(const uint32_t* p) {
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void spl_st_release(uint32_t* p, uint32_t v) {
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// `steps` lock-steps of uniform-random-legal play with same-step auto-reset in ONE launch: a warp keeps its
+// 32 games in registers for the lock-steps of a work unit and streams each step's observation / mask / reward /
+// terminated / action into [steps][n][...] rollout buffers.  Bit-identical to `steps` calls of spl_step chained
+// through next_action, whatever the schedule.  p.scratch: [0] = unit counter, [4 + g] = lock-steps completed by
+// group g (zeroed by the launcher).
 template <int WPC>
-__global__ void __launch_bounds__(WPC * 32) spl_rollout_kernel(const StepParams p) {
+__global__ void __launch_bounds__(WPC * 32, 20 / WPC) spl_rollout_kernel(const StepParams p) {
 	__shared__ SplTables Ts;
 	__shared__ __align__(16) uint32_t tiles[WPC][SPL_TILE_WORDS];
+	__shared__ uint32_t s_unit;
 	SplTile tl;
 	tl.T = spl_stage_tables(&Ts);
 	tl.lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	tl.smem = tiles[warp];
 	const int64_t ntiles = (p.n + 31) >> 5;
+	const uint32_t groups = (uint32_t)((ntiles + WPC - 1) / WPC);
+	const uint32_t total = groups * (uint32_t)p.nchunks;
 	const uint64_t t0 = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
+	uint32_t* const queue = reinterpret_cast<uint32_t*>(p.scratch);
+	uint32_t* const done = queue + 4;
 
-	// CTA-uniform trip count (tile groups of WPC) so that the optional per-step barrier is safe
-	for (int64_t tg = blockIdx.x; tg * WPC < ntiles; tg += gridDim.x) {
-		tl.ti = tg * WPC + warp;
+	for (;;) {
+		if (threadIdx.x == 0) s_unit = atomicAdd(queue, 1u);
+		__syncthreads();
+		const uint32_t u = s_unit;
+		if (u >= total) break;  // CTA-uniform
+		const uint32_t c = u / groups, tg = u - c * groups;
+		int start, len;
+		spl_chunk_bounds((int)c, p.steps, p.chunk, start, len);
+		if (start > 0) {  // the group's previous chunk must have published its state (almost always long ago)
+			if (threadIdx.x == 0)
+				while (spl_ld_acquire(done + tg) < (uint32_t)start) __nanosleep(100);
+			__syncthreads();
+		}
+		tl.ti = (int64_t)tg * WPC + warp;
 		const int64_t env = tl.ti * 32 + tl.lane;
 		const bool valid = env < p.n;
 		tl.rows = (int)max((int64_t)0, min((int64_t)32, p.n - tl.ti * 32));
 		uint32_t w[16];
-		spl_load_state(p, env, valid, w);
+		if (valid) {  // L2 loads: the rows may have been written by another SM a moment ago
+#pragma unroll
+			for (int pl = 0; pl < SPL_STATE_PLANES; pl++) {
+				uint4 v = __ldcg(p.state + pl * p.stride + env);
+				w[4 * pl + 0] = v.x, w[4 * pl + 1] = v.y, w[4 * pl + 2] = v.z, w[4 * pl + 3] = v.w;
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 16; k++) w[k] = 0;
+		}
 		SplState s;
 		spl_unpack(w, s);
-		int32_t action = valid ? p.actions[env] : 0;
+		int32_t action = 0;
+		if (valid) action = start == 0 ? p.actions[env] : __ldcg(p.next_action + (int64_t)start * p.n + env);
 		uint32_t tops = valid ? spl_deck_tops(s, p.decks + env * SPL_DECK_STRIDE) : 0xFFFFFFu;
 		// rotated loop: [legal mask of the current state] -> [emit the outputs of the previous step] -> [step].
 		// The mask is needed twice -- as the action mask returned by step t-1 and as the legality check of
 		// step t (envs/splendor_env.py:55,64,81) -- and is computed once; one code copy keeps the hot loop small.
-		for (int st = 0; st <= p.steps; st++) {
+		for (int st = start; st <= start + len; st++) {
 			if (p.sync) __syncthreads();
 			const uint64_t m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, tl.T);
-			if (st > 0) {
+			if (st > start) {
 				const int64_t o = (int64_t)(st - 1) * p.n;
 				action = spl_tile_emit(p, tl, s, w, env, valid, p.obs ? p.obs + o * SPL_OBS_DIM : nullptr,
 				                       p.mask ? p.mask + o * SPL_NUM_ACTIONS : nullptr, p.next_action + o + p.n, t0 + (uint64_t)(st - 1), m);
 			}
-			if (st == p.steps) break;
+			if (st == start + len) break;
 			const int64_t o = (int64_t)st * p.n;
 			SplStepResult r;
 			spl_tile_step<true>(p, tl, s, valid, action, env, r, m, &tops);
@@ -460,6 +513,11 @@ __global__ void __launch_bounds__(WPC * 32) spl_rollout_kernel(const StepParams 
 			}
 		}
 		if (valid) spl_store_state(p, env, w);
+		__syncthreads();  // all state / next_action stores of the CTA are ordered before the publication below
+		if (threadIdx.x == 0 && start + len < p.steps) {
+			__threadfence();
+			spl_st_release(done + tg, (uint32_t)(start + len));
+		}
 	}
 }
 
@@ -907,29 +965,46 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;  // 128-bit tile stores
 	p.steps = 1;
 	p.sync = 0;
+	p.chunk = 1, p.nchunks = 1;
 }
 
-// Launch shape.  Few tiles (every warp resident at once, e.g. 65,536 envs = 2,048 tiles): 1-warp CTAs spread the
-// tiles evenly over the 148 SMs and no barrier is used (the run is latency-bound).  Many tiles: 4-warp CTAs,
-// persistent over tile groups; the rollout kernel then adds one CTA barrier per lock-step, which keeps the
-// warps of a CTA in the same code region (the kernels are instruction-fetch sensitive: ~37 KB of hot SASS).
+// Launch shape.  Single-step kernels: 4-warp CTAs, persistent over tiles (the 2 KB table staging is paid per
+// CTA per launch).  Rollout kernel: persistent CTAs pulling (tile group, step chunk) units from the work queue;
+// 1-warp CTAs when every tile can be resident at once (e.g. 65,536 envs = 2,048 tiles: one CTA per tile spreads
+// them evenly and the balancing comes from tiles migrating between SMs from chunk to chunk), 4-warp CTAs at full
+// occupancy otherwise.  Measured on B200 (tools/sweep_rollout.py): fewer CTAs than tile groups is slower (the
+// fast SMs are latency-bound and need the warps), a CTA barrier per lock-step no longer pays once the queue
+// balances the SMs, chunk lengths between 8 and 16 lock-steps are equivalent within 2 %.
 struct LaunchShape {
-	int wpc, grid, sync;
+	int wpc, grid, sync, chunk;
 };
+
+static int env_int(const char* name, int dflt) {
+	const char* e = getenv(name);
+	return e ? atoi(e) : dflt;
+}
 
 static LaunchShape launch_shape(int64_t n, int kernel) {
 	const int64_t ntiles = (n + 31) / 32;
 	LaunchShape L;
-	const char* e = getenv("SPL_WPC");
 	int64_t resident4 = (int64_t)g_num_sms * g_occ[kernel][1] * 4;
-	// single-step kernels always use 4-warp CTAs (the 2 KB table staging is paid per CTA per launch)
-	L.wpc = kernel != 2 ? 4 : (e ? atoi(e) : (ntiles <= resident4 ? 1 : 4));
+	L.wpc = kernel != 2 ? 4 : env_int("SPL_WPC", ntiles <= resident4 ? 1 : 4);
 	if (L.wpc != 1) L.wpc = 4;
 	int64_t ctas = (ntiles + L.wpc - 1) / L.wpc;
 	int64_t cap = (int64_t)g_num_sms * g_occ[kernel][L.wpc == 1 ? 0 : 1];
 	L.grid = (int)(ctas < cap ? ctas : cap);
-	const char* sy = getenv("SPL_ROLLOUT_SYNC");
-	L.sync = sy ? atoi(sy) : (L.wpc == 4 && ctas > cap);
+	L.sync = 0;
+	L.chunk = 1;
+	if (kernel == 2) {
+		L.sync = env_int("SPL_ROLLOUT_SYNC", 0);
+		L.chunk = env_int("SPL_ROLLOUT_CHUNK", ctas <= cap ? 8 : 12);  // measured: flat between 8 and 16
+		if (L.chunk < 1) L.chunk = 1;
+		const int per_sm = env_int("SPL_ROLLOUT_CTAS_PER_SM", 0);
+		if (per_sm > 0) {
+			cap = (int64_t)g_num_sms * per_sm;
+			L.grid = (int)(ctas < cap ? ctas : cap);
+		}
+	}
 	return L;
 }
 
@@ -977,7 +1052,13 @@ int spl_rollout_random(const spl_envs_t* envs, const spl_step_io_t* io, int32_t 
 	if (envs->n % 16 != 0) p.vec_ok = 0;
 	LaunchShape L = launch_shape(envs->n, 2);
 	p.sync = L.sync;
+	p.chunk = L.chunk;
+	p.nchunks = spl_num_chunks(steps, L.chunk);
 	cudaStream_t st = (cudaStream_t)stream;
+	// work queue: unit counter + per-group progress, in the scratch list (n + 4 words >= 4 + groups)
+	const int64_t groups = ((envs->n + 31) / 32 + L.wpc - 1) / L.wpc;
+	if (groups * (int64_t)p.nchunks >= (int64_t)1 << 32) return SPL_E_BADARG;
+	SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, (size_t)(4 + groups) * sizeof(int32_t), st));
 	const bool timed = g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
 	if (L.wpc == 1) spl_rollout_kernel<1><<<L.grid, 32, 0, st>>>(p);

@@ -82,4 +82,8 @@ void emu_env_step(const int32_t* row, int32_t action, int32_t* row_out, int32_t*
 	*info = (uint8_t)r.info;
 	spl_export_row(s, deck, row_out);
 }
+
+// rollout work-unit chunking: chunk c of a `steps`-step rollout -> [start, start + len)
+int emu_chunk_bounds(int c, int steps, int chunk, int* start, int* len) { return spl_chunk_bounds(c, steps, chunk, *start, *len) ? 1 : 0; }
+int emu_num_chunks(int steps, int chunk) { return spl_num_chunks(steps, chunk); }
 }

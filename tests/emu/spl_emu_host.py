@@ -68,3 +68,15 @@ def ret_table():
 
 def mt_block(seed, blk):
     return int(lib().emu_mt_block(seed, blk))
+
+
+def chunks(steps, chunk):
+    """All (start, len) work-unit chunks of a `steps`-step rollout (spl_chunk_bounds)."""
+    L = lib()
+    out, c = [], 0
+    s, n = C.c_int(), C.c_int()
+    while L.emu_chunk_bounds(c, steps, chunk, C.byref(s), C.byref(n)):
+        out.append((s.value, n.value))
+        c += 1
+    assert L.emu_num_chunks(steps, chunk) == c
+    return out

@@ -86,3 +86,18 @@ def test_random_games_vs_oracle(oracle):
             if want[4]:
                 break
     assert steps > 8000
+
+
+def test_rollout_chunking_partitions_the_steps():
+    """The rollout kernel's work units: chunks tile [0, steps) exactly, in order, full-size first and a halving tail."""
+    for steps in list(range(1, 70)) + [128, 150, 1000]:
+        for chunk in (1, 2, 3, 8, 16, 64):
+            ch = emu.chunks(steps, chunk)
+            pos = 0
+            for s, n in ch:
+                assert s == pos and n >= 1
+                pos += n
+            assert pos == steps
+            assert all(n <= 2 * chunk for _, n in ch)
+            assert ch[-1][1] <= 3  # short last unit -> short tail of the launch
+            assert len(ch) <= steps // chunk + 8

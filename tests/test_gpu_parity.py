@@ -366,6 +366,37 @@ def test_rollout_kernel_equals_chained_steps(VecEnv, oracle, n):
     assert int(a.stats[0]) > 0
 
 
+@pytest.mark.parametrize("chunk,wpc,ctas_per_sm", [(1, 1, 0), (3, 4, 0), (8, 4, 1), (16, 1, 2), (64, 4, 0), (5, 1, 20)])
+def test_rollout_schedule_independence(VecEnv, monkeypatch, chunk, wpc, ctas_per_sm):
+    """The rollout kernel pulls (tile group, step chunk) work units from an atomic queue; its outputs must not depend on
+    the chunk length, the CTA shape or the number of CTAs (i.e. on which SM ran which chunk, and in what order)."""
+    n, T = 4096 + 48, 70
+
+    def run():
+        e = VecEnv(n, seed=77, shuffle="philox", autoreset=True)
+        e.reset()
+        acts = torch.zeros((T + 1, n), dtype=torch.int32, device="cuda")
+        acts[0] = e.sample_random_actions()
+        obs = torch.zeros((T, n, 297), dtype=torch.int32, device="cuda")
+        mask = torch.zeros((T, n, 45), dtype=torch.int8, device="cuda")
+        rew = torch.zeros((T, n), dtype=torch.float32, device="cuda")
+        term = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+        info = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+        e.rollout_random(T, acts[0], obs=obs, mask=mask, reward=rew, terminated=term, next_actions=acts, info=info)
+        torch.cuda.synchronize()
+        return obs, mask, rew, term, info, acts, e.export_state(), e.stats.clone(), e.episode.clone()
+
+    ref = run()
+    monkeypatch.setenv("SPL_ROLLOUT_CHUNK", str(chunk))
+    monkeypatch.setenv("SPL_WPC", str(wpc))
+    if ctas_per_sm:
+        monkeypatch.setenv("SPL_ROLLOUT_CTAS_PER_SM", str(ctas_per_sm))
+    out = run()
+    for a, b in zip(ref, out):
+        assert torch.equal(a, b)
+    assert int(ref[7][0]) > 0
+
+
 def test_fused_reset_equals_reset_kernel(VecEnv):
     """The in-step Philox deal and spl_reset(reset_mask=...) produce the same new episode for (seed, env, episode)."""
     n, T = 4096, 120
