@@ -993,6 +993,8 @@ static LaunchShape launch_shape(int64_t n, int kernel) {
 	int64_t ctas = (ntiles + L.wpc - 1) / L.wpc;
 	int64_t cap = (int64_t)g_num_sms * g_occ[kernel][L.wpc == 1 ? 0 : 1];
 	L.grid = (int)(ctas < cap ? ctas : cap);
+	if (kernel != 2 && env_int("SPL_STEP_PERSISTENT", 0) == 0) L.grid = (int)ctas;  // one tile group per CTA: the hardware
+	                                                                                  // CTA scheduler balances the SMs
 	L.sync = 0;
 	L.chunk = 1;
 	if (kernel == 2) {
