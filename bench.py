@@ -400,73 +400,93 @@ def run_b200(args):
                     "us_per_lock_step": 1e3 * lms / (k2 * T)}
         del g2
 
-    # ---- end-to-end through the public API with HOST buffers (H2D actions, D2H everything the reference's step returns)
+    # ---- end-to-end through the public API with HOST buffers: SplendorVecEnv.step_host (C ABI spl_host_step).
+    # Every lock-step: actions from host memory -> device, step kernel, results -> host memory as the reference-typed
+    # arrays (int32 obs, int8 mask, float reward, bool terminated) -- all inside the timed region.
     e2e = None
+    e2e_u8 = None
     e2e_light = None
+    e2e_plain = None
     if not args.skip_e2e:
-        env2 = env
-        h_act = torch.zeros(N, dtype=torch.int32).pin_memory()
-        h_obs = torch.zeros((N, 297), dtype=torch.int32).pin_memory()
-        h_mask = torch.zeros((N, 45), dtype=torch.int8).pin_memory()
-        h_rew = torch.zeros(N, dtype=torch.float32).pin_memory()
-        h_term = torch.zeros(N, dtype=torch.uint8).pin_memory()
-        h_next = torch.zeros(N, dtype=torch.int32).pin_memory()
-        d_act = torch.zeros(N, dtype=torch.int32, device=dev)
-        h_act.copy_(act_buf[0])
-        torch.cuda.synchronize()
+        import numpy as np
+
         n_e2e = max(20, min(200, 4 * T))
+        h_act = act_buf[0].cpu().numpy().copy()
 
-        def host_step():
-            d_act.copy_(h_act, non_blocking=True)
-            obs, rew, term, _, info = env2.step(d_act, sample_next=True)
-            h_obs.copy_(obs, non_blocking=True)
-            h_mask.copy_(env2.mask, non_blocking=True)
-            h_rew.copy_(rew, non_blocking=True)
-            h_term.copy_(env2._terminated, non_blocking=True)
-            h_next.copy_(env2.next_action, non_blocking=True)
+        def time_host_loop(step_fn, reps):
+            for _ in range(5):
+                step_fn()
             torch.cuda.synchronize()
-            h_act.copy_(h_next)  # the host-side "policy": actions come back from host memory every step
-
-        for _ in range(5):
-            host_step()
-        if world > 1:
-            dist.barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(n_e2e):
-            host_step()
-        a1.record()
-        torch.cuda.synchronize()
-        ems = a0.elapsed_time(a1)
-        if world > 1:
-            t = torch.tensor([ems], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
-        # informational: the same API with the observation / mask left on the device (a GPU-resident policy consumes them
-        # there); only the actions come from, and the rewards / terminations go to, pinned host memory every step
-        def host_step_light():
-            d_act.copy_(h_act, non_blocking=True)
-            env2.step(d_act, sample_next=True)
-            h_rew.copy_(env2.reward, non_blocking=True)
-            h_term.copy_(env2._terminated, non_blocking=True)
-            h_next.copy_(env2.next_action, non_blocking=True)
+            if world > 1:
+                dist.barrier()
+            t0_ = time.perf_counter()
+            for _ in range(reps):
+                step_fn()
             torch.cuda.synchronize()
-            h_act.copy_(h_next)
+            el = (time.perf_counter() - t0_) * 1e3  # host-blocking API: wall clock around the loop == device + host work
+            if world > 1:
+                t = torch.tensor([el], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                el = float(t.item())
+            return el
 
-        for _ in range(5):
-            host_step_light()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(n_e2e):
-            host_step_light()
-        c1.record()
-        torch.cuda.synchronize()
-        lms_ = c0.elapsed_time(c1)
-        e2e_light = {"value": N * n_e2e / (lms_ * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 9 * N,
-                     "what": "per GPU; obs/mask stay in HBM, actions from and rewards/terminations/next actions to pinned host memory each step"}
+        def host_step(dtype):
+            def f():
+                _o, _r, _t, _tr, info = env.step_host(h_act, obs_dtype=dtype, sample_next=True)
+                np.copyto(h_act, info["next_action"].numpy())  # the host-side "policy": actions come back from host memory
+            return f
+
+        launches_e2e0 = lib.spl_launch_count()
+        ems = time_host_loop(host_step(torch.int32), n_e2e)
+        launches_e2e = (lib.spl_launch_count() - launches_e2e0) // (n_e2e + 5)
         e2e = {"value": N * n_e2e * world / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N,
-               "d2h_bytes_per_step": N * (1188 + 45 + 4 + 1 + 4), "lock_steps": n_e2e,
-               "api": "SplendorVecEnv.step(actions) with pinned host actions in, obs/mask/reward/terminated/next-actions out to pinned host memory"}
+               "d2h_bytes_per_step": N * (297 + 16), "lock_steps": n_e2e, "us_per_lock_step": 1e3 * ems / n_e2e,
+               "host_bytes_written_per_step": N * (1188 + 45 + 4 + 1 + 1 + 4), "host_threads": int(lib.spl_host_set_threads(0)),
+               "kernels_per_lock_step": int(launches_e2e),
+               "api": "SplendorVecEnv.step_host(actions) = C ABI spl_host_step: host int32 actions in; host int32 obs [N,297], int8 mask "
+                      "[N,45], float reward, bool terminated, info bits, next actions out. PCIe carries the compact form (297 B obs "
+                      "bytes + 16 B record per env); host threads widen chunk c while chunk c+1 is in flight"}
+        ums = time_host_loop(host_step(torch.uint8), n_e2e)
+        e2e_u8 = {"value": N * n_e2e * world / (ums * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": N * (297 + 16),
+                  "what": "same call with obs_dtype=uint8: the observation stays bytes on the host (same values; the policy casts to float anyway)"}
+
+        # reference-typed arrays copied as they are (what round 1 first measured): PCIe-bound at 1,243 B per env-step
+        p_obs = torch.zeros((N, 297), dtype=torch.int32).pin_memory()
+        p_mask = torch.zeros((N, 45), dtype=torch.int8).pin_memory()
+        p_rew = torch.zeros(N, dtype=torch.float32).pin_memory()
+        p_term = torch.zeros(N, dtype=torch.uint8).pin_memory()
+        p_next = torch.zeros(N, dtype=torch.int32).pin_memory()
+        p_act = torch.from_numpy(h_act.copy()).pin_memory()
+        d_act = torch.zeros(N, dtype=torch.int32, device=dev)
+
+        def plain_step():
+            d_act.copy_(p_act, non_blocking=True)
+            obs, rew, term, _, info = env.step(d_act, sample_next=True)
+            p_obs.copy_(obs, non_blocking=True)
+            p_mask.copy_(env.mask, non_blocking=True)
+            p_rew.copy_(rew, non_blocking=True)
+            p_term.copy_(env._terminated, non_blocking=True)
+            p_next.copy_(env.next_action, non_blocking=True)
+            torch.cuda.synchronize()
+            p_act.copy_(p_next)
+
+        pms = time_host_loop(plain_step, max(20, n_e2e // 4))
+        e2e_plain = {"value": N * max(20, n_e2e // 4) * world / (pms * 1e-3), "unit": UNIT, "d2h_bytes_per_step": N * (1188 + 45 + 4 + 1 + 4),
+                     "what": "step() + torch copies of the int32/int8/float arrays to pinned memory (no compact form): PCIe-bound"}
+
+        # informational: observation / mask left on the device (a GPU-resident policy consumes them there)
+        def light_step():
+            d_act.copy_(p_act, non_blocking=True)
+            env.step(d_act, sample_next=True)
+            p_rew.copy_(env.reward, non_blocking=True)
+            p_term.copy_(env._terminated, non_blocking=True)
+            p_next.copy_(env.next_action, non_blocking=True)
+            torch.cuda.synchronize()
+            p_act.copy_(p_next)
+
+        lms_ = time_host_loop(light_step, n_e2e)
+        e2e_light = {"value": N * n_e2e * world / (lms_ * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 9 * N,
+                     "what": "obs/mask stay in HBM, actions from and rewards/terminations/next actions to pinned host memory each step"}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only)
     cpu = None
@@ -494,7 +514,7 @@ def run_b200(args):
                 "cuda_graph": graph is not None, "parallelism": f"env-sharded x{world}, no collective on the step path",
                 "l2": "rollout buffer %.1f GB per GPU is larger than the 126 MB L2; no flush" % (T * per_step_bytes / 1e9),
             },
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_device_obs": e2e_light, "lockstep": lockstep,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_u8_obs": e2e_u8, "e2e_plain_copies": e2e_plain, "e2e_device_obs": e2e_light, "lockstep": lockstep,
             "gpu_launches": int(launches_per_segment * K), "clocks": clocks,
             "episode_stats": dict(zip(L.STAT_NAMES, st)),
         }

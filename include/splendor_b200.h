@@ -57,6 +57,13 @@ extern "C" {
 #define SPL_STAT_SUM_MOVES 6
 #define SPL_STAT_SUM_WINNER_PRESTIGE 7
 
+/* reward constants of envs/splendor_env.py:61-80 as codes (compact device->host record, spl_host_step) */
+#define SPL_REWARD_CODE_ZERO 0u    /*  0.0  */
+#define SPL_REWARD_CODE_WIN 1u     /* +1.0  */
+#define SPL_REWARD_CODE_LOSS 2u    /* -1.0  */
+#define SPL_REWARD_CODE_LIMIT 3u   /* -0.1  turn-limit draw (:75-76) */
+#define SPL_REWARD_CODE_ILLEGAL 4u /* -0.01 illegal action (:64-66) */
+
 #define SPL_E_BADARG (-1)
 #define SPL_E_NOTINIT (-2)
 #define SPL_E_ALIGN (-3)
@@ -179,6 +186,45 @@ int spl_masked_sample(const float *logits, const int8_t *mask, int64_t n, int mo
 /* generalised advantage estimation over step-major [T][n] buffers (ppo_splendor.py:299-314) */
 int spl_gae(const float *rewards, const float *values, const uint8_t *terminals, const float *last_values, int32_t T,
             int64_t n, float gamma, float lam, float *advantages, float *returns, void *stream);
+
+/* ---- host-buffer entry points ---------------------------------------------------------------------
+ * The reference's callers live on the host: SplendorEnv.step returns NumPy arrays (envs/splendor_env.py:51-90)
+ * and the vector loop stacks them (ppo_splendor.py:235-285).  These calls take HOST pointers for actions and
+ * results.  Per lock-step they move 4 B/env to the device and 313 B/env back (observation as bytes + one
+ * 16-byte record: 45 legal-mask bits, reward code, terminated, info, sampled next action) instead of the
+ * 1,243 B/env of the reference-typed arrays; the device->host copy is cut into chunks and host threads widen
+ * chunk c (uint8 -> int32 observation, bits -> int8 mask, code -> float reward) while chunk c+1 is in flight.
+ * Results in the caller's buffers are exactly those of spl_step / spl_observe. */
+typedef struct spl_host spl_host_t; /* opaque: compact device buffers, pinned staging, events */
+
+typedef struct spl_host_io {
+	const int32_t *actions; /* [n] host (ignored by spl_host_observe) */
+	int32_t *obs;           /* [n][297] host, nullable */
+	uint8_t *obs_u8;        /* [n][297] host, nullable: the same observation as bytes (all entries < 256) */
+	int8_t *mask;           /* [n][45] host, nullable */
+	float *reward;          /* [n] host, nullable */
+	uint8_t *terminated;    /* [n] host, nullable */
+	uint8_t *info;          /* [n] host, nullable: SPL_INFO_* */
+	int32_t *next_action;   /* [n] host, nullable: uniform random legal action for the returned mask */
+	int64_t *stats;         /* [8] DEVICE, nullable */
+	uint64_t action_key;    /* Philox key / lock-step counter of next_action */
+	uint64_t action_t;
+	int32_t autoreset;
+	int32_t reserved_;
+} spl_host_io_t;
+
+int spl_host_create(int64_t n, int32_t chunks, spl_host_t **out); /* chunks <= 0: library default */
+int spl_host_destroy(spl_host_t *h);
+/* SplendorEnv.step for every env with host buffers; returns when the caller's buffers are filled */
+int spl_host_step(spl_host_t *h, const spl_envs_t *envs, const spl_host_io_t *io, void *stream);
+/* observation / mask (/ sampled action) of the current states into host buffers (after spl_reset) */
+int spl_host_observe(spl_host_t *h, const spl_envs_t *envs, const spl_host_io_t *io, void *stream);
+/* the widening step alone, for callers that move the compact records themselves: obs_u8 [n][297] and side [n][16 B]
+ * (word 0 = mask bits 0-31; word 1 = mask bits 32-44 | reward code << 16 | terminated << 24; word 2 = info |
+ * next action << 8) in HOST memory -> the non-NULL host arrays of `io`.  Pure CPU; needs no device. */
+int spl_host_expand(const uint8_t *obs_u8, const void *side, int64_t n, const spl_host_io_t *io);
+/* host threads used for widening (default: the cores this process may run on, at most 32); returns the count */
+int spl_host_set_threads(int n);
 
 const char *spl_error_string(int code);
 int spl_version(void);

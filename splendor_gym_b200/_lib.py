@@ -36,6 +36,7 @@ EXPORTS = (
     "spl_init", "spl_reset", "spl_step", "spl_observe", "spl_random_action", "spl_export_state", "spl_import_state",
     "spl_dual_combine", "spl_error_string", "spl_version", "spl_host_ret_table", "spl_launch_count",
     "spl_timing_enable", "spl_timing_read", "spl_rollout_random", "spl_scripted_action", "spl_masked_sample", "spl_gae",
+    "spl_host_create", "spl_host_destroy", "spl_host_step", "spl_host_observe", "spl_host_set_threads", "spl_host_expand",
 )
 
 BOT_RANDOM, BOT_GREEDY_V1, BOT_BASIC_PRIORITY, BOT_GREEDY_V2 = 0, 1, 2, 3
@@ -59,6 +60,17 @@ class SplStepIO(C.Structure):
         ("reward", C.c_void_p), ("terminated", C.c_void_p), ("info", C.c_void_p), ("stats", C.c_void_p),
         ("next_action", C.c_void_p), ("action_key", C.c_uint64), ("action_t", C.c_uint64),
         ("action_t_base", C.c_void_p), ("autoreset", C.c_int32), ("reserved_", C.c_int32),
+    ]
+
+
+class SplHostIO(C.Structure):
+    """struct spl_host_io (include/splendor_b200.h): HOST pointers (stats: device)."""
+
+    _fields_ = [
+        ("actions", C.c_void_p), ("obs", C.c_void_p), ("obs_u8", C.c_void_p), ("mask", C.c_void_p),
+        ("reward", C.c_void_p), ("terminated", C.c_void_p), ("info", C.c_void_p), ("next_action", C.c_void_p),
+        ("stats", C.c_void_p), ("action_key", C.c_uint64), ("action_t", C.c_uint64),
+        ("autoreset", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -115,6 +127,18 @@ def load():
     L.spl_timing_enable.argtypes = [C.c_int]
     L.spl_timing_read.restype = C.c_int
     L.spl_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.spl_host_create.restype = C.c_int
+    L.spl_host_create.argtypes = [i64, C.c_int32, C.POINTER(vp)]
+    L.spl_host_destroy.restype = C.c_int
+    L.spl_host_destroy.argtypes = [vp]
+    L.spl_host_step.restype = C.c_int
+    L.spl_host_step.argtypes = [vp, C.POINTER(SplEnvs), C.POINTER(SplHostIO), vp]
+    L.spl_host_observe.restype = C.c_int
+    L.spl_host_observe.argtypes = [vp, C.POINTER(SplEnvs), C.POINTER(SplHostIO), vp]
+    L.spl_host_expand.restype = C.c_int
+    L.spl_host_expand.argtypes = [vp, vp, i64, C.POINTER(SplHostIO)]
+    L.spl_host_set_threads.restype = C.c_int
+    L.spl_host_set_threads.argtypes = [C.c_int]
     _lib = L
     return L
 

@@ -139,6 +139,25 @@ __device__ __forceinline__ void spl_store_obs_tile(int32_t* gtile, const uint32_
 	}
 }
 
+// the staged tile IS the byte image of the [32][297] uint8 observation tile: 594 int4 per warp (host path)
+__device__ __forceinline__ void spl_store_obs_tile_u8(uint8_t* gtile, const uint32_t* tile, int lane, int rows, bool vec) {
+	if (rows == 32 && vec) {
+		const int4* t4 = reinterpret_cast<const int4*>(tile);
+		int4* g4 = reinterpret_cast<int4*>(gtile);
+#pragma unroll 2
+		for (int q = lane; q < SPL_TILE_WORDS / 4; q += 32) __stcs(g4 + q, t4[q]);
+	} else {
+		const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+		for (int e = lane; e < rows * SPL_OBS_DIM; e += 32) gtile[e] = tb[e];
+	}
+}
+
+// reward of envs/splendor_env.py:61-80 as a small code (the host path moves one byte, not a float)
+__device__ __forceinline__ uint32_t spl_reward_code(float r) {
+	return r == 0.0f ? SPL_REWARD_CODE_ZERO : r == 1.0f ? SPL_REWARD_CODE_WIN : r == -1.0f ? SPL_REWARD_CODE_LOSS
+	     : r == -0.1f ? SPL_REWARD_CODE_LIMIT : SPL_REWARD_CODE_ILLEGAL;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Native (Philox) deal: a uniformly random permutation of each deck and of the nobles by SORTING
 // RANDOM KEYS, done by the whole warp for ONE environment (the rest of the warp would otherwise idle
@@ -249,6 +268,8 @@ struct StepParams {
 	int vec_ok;  // obs / mask bases are 16-byte aligned (and, for step-major buffers, every step's slice is)
 	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
 	int sync;    // rollout kernel: CTA barrier per lock-step (keeps the warps of a CTA in the same code region)
+	uint8_t* obs_u8;  // compact outputs (host path, spl_host.cu): observation tile as bytes [n][297] ...
+	uint4* side;      // ... and one 16-byte record per env: legal-mask bits, reward code, terminated, info, sampled action
 	int chunk, nchunks;  // rollout kernel: lock-steps per work unit, chunks per tile group (spl_chunk_bounds)
 };
 
@@ -370,8 +391,11 @@ __device__ __forceinline__ const SplTables* spl_stage_tables(SplTables* T) {
 	return T;
 }
 
-// one lock-step (DO_STEP) or just encode_observation + legal_moves of the current states
-template <bool DO_STEP, int WPC>
+// one lock-step (DO_STEP) or just encode_observation + legal_moves of the current states.
+// COMPACT (host path): outputs are the uint8 observation tile + one 16-byte record per env instead of the
+// reference-typed int32 / int8 / float arrays -- 313 B instead of 1,243 B per env-step cross PCIe and the host
+// widens them (spl_host_expand.cpp).
+template <bool DO_STEP, int WPC, bool COMPACT>
 __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) {
 	__shared__ SplTables Ts;
 	__shared__ __align__(16) uint32_t tiles[WPC][SPL_TILE_WORDS];
@@ -391,23 +415,36 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 		spl_load_state(p, env, valid, w);
 		SplState s;
 		spl_unpack(w, s);
+		SplStepResult r;
+		r.reward = 0.0f, r.terminated = 0, r.info = 0;
 		if (DO_STEP) {
 			const bool act = valid && (p.active == nullptr || p.active[env] != 0);
-			SplStepResult r;
 			spl_tile_step<false>(p, tl, s, act, act ? p.actions[env] : 0, env, r);
 			if (act) {
 				spl_pack(s, w);
 				spl_store_state(p, env, w);
 			}
-			if (valid) {
+			if (valid && !COMPACT) {
 				p.reward[env] = r.reward;
 				p.terminated[env] = (uint8_t)r.terminated;
 				p.info[env] = (uint8_t)r.info;
 			}
 		}
 		uint64_t m = 0;
-		if (p.mask != nullptr || p.next_action != nullptr) m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, tl.T);
-		spl_tile_emit(p, tl, s, w, env, valid, p.obs, p.mask, p.next_action, t, m);
+		if (COMPACT || p.mask != nullptr || p.next_action != nullptr) m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, tl.T);
+		if (COMPACT) {
+			const int32_t sampled = spl_sample_action(m, p.action_key, p.env_offset + (uint64_t)env, t);
+			SplObsStager stage(tl.smem, tl.lane, w[0]);
+			spl_encode_observation(w, s, tl.T, stage);
+			__syncwarp();
+			spl_store_obs_tile_u8(p.obs_u8 + tl.ti * 32 * SPL_OBS_DIM, tl.smem, tl.lane, tl.rows, p.vec_ok);
+			__syncwarp();
+			if (valid)
+				__stcs(p.side + env, make_uint4((uint32_t)m, (uint32_t)(m >> 32) | (spl_reward_code(r.reward) << 16) | ((uint32_t)r.terminated << 24),
+				                               (uint32_t)r.info | ((uint32_t)sampled << 8), 0u));
+		} else {
+			spl_tile_emit(p, tl, s, w, env, valid, p.obs, p.mask, p.next_action, t, m);
+		}
 	}
 }
 
@@ -898,8 +935,10 @@ int spl_init(void) {
 	SPL_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
 	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[kid][slot], K, threads, 0));                       \
 	if (g_occ[kid][slot] < 1) g_occ[kid][slot] = 1;
-	SPL_SETUP((spl_step_kernel<true, 4>), 0, 1, 128)
-	SPL_SETUP((spl_step_kernel<false, 4>), 1, 1, 128)
+	SPL_SETUP((spl_step_kernel<true, 4, false>), 0, 1, 128)
+	SPL_SETUP((spl_step_kernel<false, 4, false>), 1, 1, 128)
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	SPL_SETUP((spl_rollout_kernel<1>), 2, 0, 32)
 	SPL_SETUP((spl_rollout_kernel<4>), 2, 1, 128)
 #undef SPL_SETUP
@@ -966,6 +1005,7 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.steps = 1;
 	p.sync = 0;
 	p.chunk = 1, p.nchunks = 1;
+	p.obs_u8 = nullptr, p.side = nullptr;
 }
 
 // Launch shape.  Single-step kernels: 4-warp CTAs, persistent over tiles (the 2 KB table staging is paid per
@@ -1016,12 +1056,35 @@ static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
-	if (do_step) spl_step_kernel<true, 4><<<L.grid, 128, 0, st>>>(p);
-	else spl_step_kernel<false, 4><<<L.grid, 128, 0, st>>>(p);
+	if (do_step) spl_step_kernel<true, 4, false><<<L.grid, 128, 0, st>>>(p);
+	else spl_step_kernel<false, 4, false><<<L.grid, 128, 0, st>>>(p);
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
 	g_launches++;
 	return (int)cudaGetLastError();
 }
+
+}  // extern "C"
+
+// internal (spl_host.cu): one lock-step (or observe) with COMPACT outputs into obs_u8 [n][297] / side [n]
+int spl_launch_compact(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, uint8_t* obs_u8, void* side, cudaStream_t st) {
+	int rc = check_envs(e);
+	if (rc) return rc;
+	if (e->shuffle_mode != SPL_SHUFFLE_PHILOX && do_step && io && io->autoreset) return SPL_E_BADARG;  // fused reset only
+	StepParams p;
+	fill_step_params(p, e, io, nullptr, nullptr);
+	p.obs_u8 = obs_u8, p.side = (uint4*)side;
+	p.vec_ok = ((uintptr_t)obs_u8 & 15) == 0;
+	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
+	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
+	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
+	if (do_step) spl_step_kernel<true, 4, true><<<L.grid, 128, 0, st>>>(p);
+	else spl_step_kernel<false, 4, true><<<L.grid, 128, 0, st>>>(p);
+	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
+	g_launches++;
+	return (int)cudaGetLastError();
+}
+
+extern "C" {
 
 int spl_step(const spl_envs_t* envs, const spl_step_io_t* io, void* stream) {
 	int rc = check_envs(envs);

@@ -120,7 +120,8 @@ class SplendorVecEnv:
         self._is_reset = False
 
     def close(self) -> None:
-        """Nothing to release beyond the tensors (kept for gymnasium.vector API parity)."""
+        """Releases the host-path staging context, if any (the tensors go with the object)."""
+        self.close_host()
 
     def episode_statistics(self) -> Dict[str, int]:
         """Counters accumulated by the step kernels since construction (one host read)."""
@@ -227,6 +228,87 @@ class SplendorVecEnv:
         with torch.cuda.device(self.device):
             L.check(self.lib.spl_rollout_random(C.byref(self._envs), C.byref(io), int(steps), self._stream()), "spl_rollout_random")
         self._t += steps
+
+    # ------------------------------------------------------------------ host-buffer API (NumPy-side callers)
+    def _host_setup(self, obs_dtype):
+        """Host result arrays (reused every call, like gym.vector's pre-allocated observation buffers) + the library's
+        staging context.  ``obs_dtype``: ``torch.int32`` = the reference's dtype (envs/splendor_env.py:34-36);
+        ``torch.uint8`` = the same values as bytes (a quarter of the host memory traffic; all entries are < 256)."""
+        H = getattr(self, "_host", None)
+        if H is not None and H["obs"].dtype == obs_dtype:
+            return H
+        n = self.n
+        if H is None:
+            handle = C.c_void_p()
+            with torch.cuda.device(self.device):
+                L.check(self.lib.spl_host_create(n, 0, C.byref(handle)), "spl_host_create")
+            H = dict(handle=handle, io=L.SplHostIO(),
+                     mask=torch.zeros((n, L.NUM_ACTIONS), dtype=torch.int8), reward=torch.zeros(n, dtype=torch.float32),
+                     terminated=torch.zeros(n, dtype=torch.uint8), info_bits=torch.zeros(n, dtype=torch.uint8),
+                     next_action=torch.zeros(n, dtype=torch.int32), truncated=torch.zeros(n, dtype=torch.bool))
+            self._host = H
+        H["obs"] = torch.zeros((n, L.OBS_DIM), dtype=obs_dtype)
+        if obs_dtype == torch.uint8:
+            H["obs"] = H["obs"].pin_memory()  # the copy engine writes the bytes straight into it
+        return H
+
+    def _host_call(self, fn, name, actions, obs_dtype, sample_next, autoreset):
+        H = self._host_setup(obs_dtype)
+        io = H["io"]
+        io.actions = actions
+        io.obs = H["obs"].data_ptr() if obs_dtype == torch.int32 else None
+        io.obs_u8 = H["obs"].data_ptr() if obs_dtype == torch.uint8 else None
+        io.mask, io.reward = H["mask"].data_ptr(), H["reward"].data_ptr()
+        io.terminated, io.info = H["terminated"].data_ptr(), H["info_bits"].data_ptr()
+        io.next_action = H["next_action"].data_ptr() if sample_next else None
+        io.stats = self.stats.data_ptr()
+        io.action_key = self.action_key
+        io.autoreset = int(autoreset)
+        with torch.cuda.device(self.device):
+            L.check(fn(H["handle"], C.byref(self._envs), C.byref(io), self._stream()), name)
+        return H
+
+    def reset_host(self, *, obs_dtype=torch.int32, sample_next: bool = False, **kw):
+        """``reset`` returning HOST tensors -> (obs [N,297], {"action_mask": int8 [N,45], "to_play": ...})."""
+        if obs_dtype not in (torch.int32, torch.uint8):
+            raise ValueError("obs_dtype must be torch.int32 or torch.uint8")
+        self.reset(**kw)
+        self._host_setup(obs_dtype)["io"].action_t = self._t
+        H = self._host_call(self.lib.spl_host_observe, "spl_host_observe", None, obs_dtype, sample_next, False)
+        return H["obs"], {"action_mask": H["mask"], "to_play": H["obs"][:, 294]}
+
+    def step_host(self, actions, *, obs_dtype=torch.int32, sample_next: bool = False, autoreset: Optional[bool] = None):
+        """``SplendorEnv.step`` for every env with HOST arrays in and out -- the call a NumPy-side vector loop makes
+        (ppo_splendor.py:235-285).  ``actions``: int32 ``numpy.ndarray`` / CPU tensor ``[N]``.  Returns CPU tensors
+        ``(obs, reward, terminated, truncated, info)`` owned by the env and overwritten by the next call;
+        ``info["next_action"]`` (with ``sample_next``) is a uniform random legal action per env for the new mask.
+        Device work: H2D actions -> step kernel (compact outputs) -> chunked D2H; host threads widen chunk c into the
+        reference-typed arrays while chunk c+1 is in flight (csrc/spl_host.cu).  Values are those of ``step``."""
+        assert self._is_reset, "Call reset() first"
+        if obs_dtype not in (torch.int32, torch.uint8):
+            raise ValueError("obs_dtype must be torch.int32 or torch.uint8")
+        autoreset = self.autoreset if autoreset is None else autoreset
+        if autoreset and self.shuffle_mode != L.SHUFFLE_PHILOX:
+            raise L.SplendorB200Error("step_host with auto-reset needs shuffle='philox' (MT19937 resets run as a second kernel; "
+                                      "use step() and copy, or autoreset=False)")
+        a = torch.as_tensor(actions)
+        if a.dtype != torch.int32 or not a.is_contiguous() or a.device.type != "cpu":
+            a = a.to(device="cpu", dtype=torch.int32).contiguous()
+        if a.numel() != self.n:
+            raise ValueError("actions must have one entry per env")
+        self._host_setup(obs_dtype)["io"].action_t = self._t + 1
+        H = self._host_call(self.lib.spl_host_step, "spl_host_step", a.data_ptr(), obs_dtype, sample_next, autoreset)
+        self._t += 1
+        info = {"action_mask": H["mask"], "to_play": H["obs"][:, 294], "info_bits": H["info_bits"]}
+        if sample_next:
+            info["next_action"] = H["next_action"]
+        return H["obs"], H["reward"], H["terminated"].view(torch.bool), H["truncated"], info
+
+    def close_host(self) -> None:
+        H = getattr(self, "_host", None)
+        if H is not None:
+            self.lib.spl_host_destroy(H["handle"])
+            self._host = None
 
     def observe(self, out_obs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None):
         """encode_observation + legal_moves of the current states (no step)."""

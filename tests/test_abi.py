@@ -46,6 +46,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.SplEnvs) == 4 * 8 + 4 * 8 + 8
     assert C.sizeof(_lib.SplStepIO) == 9 * 8 + 2 * 8 + 8 + 8
     assert _lib.SplEnvs.shuffle_mode.offset == 64 and _lib.SplStepIO.autoreset.offset == 96
+    # struct spl_host_io: 9 pointers, 2 uint64, 2 int32
+    assert C.sizeof(_lib.SplHostIO) == 9 * 8 + 2 * 8 + 8 and _lib.SplHostIO.autoreset.offset == 88
     text = open(os.path.join(ROOT, "include", "splendor_b200.h")).read()
     for name, val in (("SPL_NUM_ACTIONS", _lib.NUM_ACTIONS), ("SPL_OBS_DIM", _lib.OBS_DIM), ("SPL_ROW_LEN", _lib.ROW_LEN),
                       ("SPL_DECK_STRIDE", _lib.DECK_STRIDE), ("SPL_RET_TABLE_LEN", _lib.RET_TABLE_LEN)):
@@ -74,6 +76,44 @@ def test_argument_errors_without_gpu(lib):
     assert lib.spl_reset(C.byref(envs), None, None, None, None, None) == -1
     assert lib.spl_random_action(None, 0, 0, 0, 0, None, None) == -1
     assert lib.spl_gae(None, None, None, None, 1, 1, 0.99, 0.95, None, None, None) == -1
+
+
+@pytest.mark.parametrize("n,threads", [(1, 1), (33, 2), (1000, 4), (5001, 3)])
+def test_host_expand_widens_compact_records(lib, n, threads):
+    """spl_host_expand (host half of spl_host_step): compact records -> the reference-typed arrays, checked against
+    a NumPy restatement of the record layout; ragged sizes exercise the unaligned head / tail of the SIMD loop."""
+    from splendor_gym_b200 import _lib
+
+    rng = np.random.default_rng(n)
+    obs8 = rng.integers(0, 256, size=(n, 297), dtype=np.uint8)
+    mbits = rng.integers(0, 1 << 45, size=n, dtype=np.uint64)
+    code = rng.integers(0, 5, size=n, dtype=np.uint32)
+    term = rng.integers(0, 2, size=n, dtype=np.uint32)
+    info = rng.integers(0, 256, size=n, dtype=np.uint32)
+    act = rng.integers(0, 45, size=n, dtype=np.uint32)
+    side = np.zeros((n, 4), np.uint32)
+    side[:, 0] = (mbits & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    side[:, 1] = (mbits >> np.uint64(32)).astype(np.uint32) | (code << 16) | (term << 24)
+    side[:, 2] = info | (act << 8)
+    # offset the destination by one element so that it is NOT 32-byte aligned
+    obs_store = np.full(n * 297 + 9, -7, np.int32)
+    obs = obs_store[1:1 + n * 297].reshape(n, 297)
+    mask = np.full((n, 45), 9, np.int8)
+    guard = np.full(64, 9, np.int8)
+    rew, te, inf, nxt = np.zeros(n, np.float32), np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int32)
+    obs8_out = np.zeros((n, 297), np.uint8)
+    io = _lib.SplHostIO(obs=obs.ctypes.data, obs_u8=obs8_out.ctypes.data, mask=mask.ctypes.data, reward=rew.ctypes.data,
+                        terminated=te.ctypes.data, info=inf.ctypes.data, next_action=nxt.ctypes.data)
+    assert lib.spl_host_set_threads(threads) == threads
+    assert lib.spl_host_expand(obs8.ctypes.data, side.ctypes.data, n, C.byref(io)) == 0
+    assert np.array_equal(obs, obs8.astype(np.int32)) and obs_store[0] == -7 and np.all(obs_store[1 + n * 297:] == -7)
+    assert np.array_equal(obs8_out, obs8)
+    want_mask = ((mbits[:, None] >> np.arange(45, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.int8)
+    assert np.array_equal(mask, want_mask) and np.all(guard == 9)
+    assert np.array_equal(rew, np.array([0.0, 1.0, -1.0, -0.1, -0.01], np.float32)[code])
+    assert np.array_equal(te, term.astype(np.uint8)) and np.array_equal(inf, info.astype(np.uint8))
+    assert np.array_equal(nxt, act.astype(np.int32))
+    assert lib.spl_host_expand(None, None, n, C.byref(io)) == -1
 
 
 def test_product_package_never_touches_the_oracle():

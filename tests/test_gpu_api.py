@@ -294,3 +294,55 @@ def test_ppo_rollout_collection_small():
     vals = torch.unique(r[d]).cpu().tolist()
     assert all(min(abs(v - c) for c in (-1.0, 0.0, 1.0, -0.1)) < 1e-6 for v in vals)
     assert int(env.stats[0]) == int(d.sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,obs_dtype", [(1000, "int32"), (8192 + 32, "int32"), (4096, "uint8"), (7, "int32")])
+def test_step_host_equals_step(n, obs_dtype):
+    """The host-buffer path (spl_host_step: compact device outputs, chunked D2H, host widening) returns exactly what
+    step() returns on the device: observation, mask, reward, terminated, info bits, sampled next action, statistics."""
+    import torch
+    from splendor_gym_b200 import SplendorVecEnv
+
+    dt = getattr(torch, obs_dtype)
+    a = SplendorVecEnv(n, seed=5, shuffle="philox", autoreset=True)
+    b = SplendorVecEnv(n, seed=5, shuffle="philox", autoreset=True)
+    oa, ia = a.reset()
+    ob, ib = b.reset_host(obs_dtype=dt, sample_next=True)
+    assert ob.device.type == "cpu" and ob.dtype == dt
+    assert torch.equal(oa.cpu().to(dt), ob) and torch.equal(ia["action_mask"].cpu(), ib["action_mask"])
+    act = a.sample_random_actions().clone()
+    assert torch.equal(act.cpu(), b._host["next_action"])
+    rng = torch.Generator().manual_seed(0)
+    for t in range(70):
+        if t % 9 == 4:  # sprinkle illegal / out-of-range actions
+            bad = torch.randint(0, n, (max(1, n // 50),), generator=rng)
+            act[bad.to(act.device)] = torch.randint(-3, 60, (bad.numel(),), generator=rng, dtype=torch.int32).to(act.device)
+        h_act = act.cpu().numpy().copy()
+        o1, r1, t1, _, i1 = a.step(act, sample_next=True)
+        o2, r2, t2, tr2, i2 = b.step_host(h_act, obs_dtype=dt, sample_next=True)
+        assert torch.equal(o1.cpu().to(dt), o2), f"step {t}: obs"
+        assert torch.equal(i1["action_mask"].cpu(), i2["action_mask"]), f"step {t}: mask"
+        assert torch.equal(r1.cpu(), r2) and torch.equal(t1.cpu(), t2) and not tr2.any()
+        assert torch.equal(a.info_bits.cpu(), i2["info_bits"])
+        assert torch.equal(a.next_action.cpu(), i2["next_action"])
+        act = a.next_action.clone()
+    assert torch.equal(a.export_state(), b.export_state()) and torch.equal(a.stats, b.stats)
+    assert int(a.stats[0]) > 0 or n < 100
+    b.close()
+
+
+@pytest.mark.gpu
+def test_step_host_rejects_what_it_cannot_do():
+    import numpy as np
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200._lib import SplendorB200Error
+
+    e = SplendorVecEnv(64, seed=1, shuffle="mt19937", autoreset=True)
+    e.reset()
+    with pytest.raises(SplendorB200Error):
+        e.step_host(np.zeros(64, np.int32))
+    o, r, t, tr, info = e.step_host(np.zeros(64, np.int32), autoreset=False)  # MT19937 decks are fine without auto-reset
+    assert o.shape == (64, 297)
+    with pytest.raises(ValueError):
+        e.step_host(np.zeros(3, np.int32), autoreset=False)
