@@ -23,6 +23,9 @@
 #define SPL_DECK_SMEM 100 /* per-lane deck row in shared memory: 25 words (odd) to spread banks */
 
 __device__ SplTables g_tables;
+#ifdef SPL_DEBUG_SM_UNITS
+__device__ unsigned int g_sm_units[256];  // diagnostic build (tools/sm_units.py): warp-lock-steps processed per SM
+#endif
 __device__ uint64_t g_ret_table[SPL_RET_TABLE_LEN];
 
 // ------------------------------------------------------------------------------------------------
@@ -549,6 +552,13 @@ __global__ void __launch_bounds__(WPC * 32, 20 / WPC) spl_rollout_kernel(const S
 				if (p.info != nullptr) p.info[o + env] = (uint8_t)r.info;
 			}
 		}
+#ifdef SPL_DEBUG_SM_UNITS
+		if (tl.lane == 0) {
+			unsigned sm;
+			asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+			atomicAdd(&g_sm_units[sm], (unsigned)len);
+		}
+#endif
 		if (valid) spl_store_state(p, env, w);
 		__syncthreads();  // all state / next_action stores of the CTA are ordered before the publication below
 		if (threadIdx.x == 0 && start + len < p.steps) {
@@ -897,6 +907,17 @@ int spl_timing_read(double* total_ms, int64_t* count) {
 }
 
 int64_t spl_launch_count(void) { return g_launches; }
+
+#ifdef SPL_DEBUG_SM_UNITS
+int spl_debug_sm_units(unsigned int* out, int reset) {
+	SPL_CUDA(cudaMemcpyFromSymbol(out, g_sm_units, sizeof(unsigned int) * 256));
+	if (reset) {
+		unsigned int z[256] = {0};
+		SPL_CUDA(cudaMemcpyToSymbol(g_sm_units, z, sizeof(z)));
+	}
+	return 0;
+}
+#endif
 
 const char* spl_error_string(int code) {
 	if (code == 0) return "ok";
