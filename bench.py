@@ -352,10 +352,13 @@ def run_b200(args):
         L.check(lib.spl_timing_enable(0))
     clocks = sampler.stop() if sampler else None
     out_bytes = (1188 if write_obs else 0) + 45 + 4 + 1 + 4  # obs + mask + reward + terminated + action, per env-step
+    plan = (C.c_int32 * 6)()
+    L.check(lib.spl_rollout_plan(N, T, plan))
     if use_rollout:
         kernel = "spl_rollout_kernel"
         units_per_launch = N * T
-        bytes_per_launch = N * T * out_bytes + N * 128 + N * 4  # + packed state read once / written once + first actions
+        # + per work unit (chunk of lock-steps): packed state read + written (128 B) and the first action read (4 B)
+        bytes_per_launch = N * T * out_bytes + N * 132 * int(plan[3])
     else:
         kernel = "spl_step_kernel<true>"
         units_per_launch = N
@@ -511,6 +514,9 @@ def run_b200(args):
                             "simplified take-3 rules, mask+step only (BASELINE configs[3]), %d envs per GPU" % N,
                 "envs_per_gpu": N, "lock_steps_per_step": T, "env_steps_per_step": N * T * world, "shuffle": args.shuffle,
                 "mode": "rollout kernel (1 launch per segment)" if use_rollout else "lockstep (1 launch per lock-step)",
+                "rollout_plan": {"warps_per_cta": int(plan[0]), "ctas": int(plan[1]), "lock_steps_per_work_unit": int(plan[2]),
+                                 "work_units_per_tile_group": int(plan[3]), "tile_groups": int(plan[5]),
+                                 "scheduling": "persistent CTAs pull (tile group, step chunk) units from an atomic queue"},
                 "cuda_graph": graph is not None, "parallelism": f"env-sharded x{world}, no collective on the step path",
                 "l2": "rollout buffer %.1f GB per GPU is larger than the 126 MB L2; no flush" % (T * per_step_bytes / 1e9),
             },

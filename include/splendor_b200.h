@@ -147,6 +147,11 @@ int spl_step(const spl_envs_t *envs, const spl_step_io_t *io, void *stream);
  * Requires SPL_SHUFFLE_PHILOX and autoreset. */
 int spl_rollout_random(const spl_envs_t *envs, const spl_step_io_t *io, int32_t steps, void *stream);
 
+/* How spl_rollout_random would run `steps` lock-steps of n envs on the current device (measurement aid):
+ * out[0] warps per CTA, [1] CTAs, [2] lock-steps per work unit, [3] work units per tile group, [4] CTA barrier per
+ * lock-step, [5] tile groups.  Each work unit reloads / stores the packed state of its envs (128 B per env). */
+int spl_rollout_plan(int64_t n, int32_t steps, int32_t *out);
+
 /* encode_observation (engine/encode.py:124-187) + legal_moves (engine/rules.py:40-93) of the current
  * states, without stepping (mask is all-zero for terminal states, as in envs/splendor_env.py:81). */
 int spl_observe(const spl_envs_t *envs, int32_t *obs, int8_t *mask, void *stream);

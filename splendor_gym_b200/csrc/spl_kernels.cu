@@ -1154,6 +1154,17 @@ int spl_rollout_random(const spl_envs_t* envs, const spl_step_io_t* io, int32_t 
 	return (int)cudaGetLastError();
 }
 
+int spl_rollout_plan(int64_t n, int32_t steps, int32_t* out) {
+	if (n <= 0 || steps <= 0 || !out) return SPL_E_BADARG;
+	if (g_inited_device < 0) return SPL_E_NOTINIT;
+	LaunchShape L = launch_shape(n, 2);
+	const int64_t groups = ((n + 31) / 32 + L.wpc - 1) / L.wpc;
+	int chunk = L.chunk, nchunks = spl_num_chunks(steps, L.chunk);
+	if (4 + groups > n + 4) chunk = steps, nchunks = 1;
+	out[0] = L.wpc, out[1] = L.grid, out[2] = chunk, out[3] = nchunks, out[4] = L.sync, out[5] = (int32_t)groups;
+	return 0;
+}
+
 int spl_observe(const spl_envs_t* envs, int32_t* obs, int8_t* mask, void* stream) {
 	int rc = check_envs(envs);
 	if (rc) return rc;
