@@ -59,6 +59,10 @@ static void default_threads() {
 	int n = 0;
 	if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
 	if (n < 1) n = 1;
+	// one process per GPU (torchrun): the ranks of a node share its cores
+	const char* lws = getenv("LOCAL_WORLD_SIZE");
+	if (lws && atoi(lws) > 1) n /= atoi(lws);
+	if (n < 1) n = 1;
 	if (n > 32) n = 32;
 	const char* e = getenv("SPL_HOST_THREADS");
 	if (e && atoi(e) > 0) n = atoi(e);

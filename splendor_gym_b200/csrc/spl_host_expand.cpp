@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <omp.h>
+#include <sched.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -114,10 +115,11 @@ void spl_expand_chunks(const uint8_t* obs_u8, const uint32_t* side, const int64_
 				if (r) __atomic_store_n(&rc, r, __ATOMIC_RELAXED);
 				__atomic_store_n(&ready, c + 1, __ATOMIC_RELEASE);
 			} else {
-				while (__atomic_load_n(&ready, __ATOMIC_ACQUIRE) <= c) {
+				for (unsigned spins = 0; __atomic_load_n(&ready, __ATOMIC_ACQUIRE) <= c; spins++) {
 #if defined(__x86_64__)
 					_mm_pause();
 #endif
+					if ((spins & 1023u) == 1023u) sched_yield();  // oversubscribed hosts: let thread 0 run
 				}
 			}
 			if (__atomic_load_n(&rc, __ATOMIC_RELAXED)) continue;
