@@ -27,6 +27,7 @@ extern "C" {
 
 #define SPL_NUM_ACTIONS 45 /* engine/encode.py:32 TOTAL_ACTIONS */
 #define SPL_OBS_DIM 297    /* engine/encode.py:74 OBSERVATION_DIM */
+#define SPL_OBS_F16_PITCH 304 /* row pitch of the fp16 policy-input observation (297 rounded up to a multiple of 8) */
 #define SPL_ROW_LEN 166    /* flat int32 debug row, see SPL_ROW_* below */
 #define SPL_STATE_PLANES 4 /* packed hot state: 4 planes of 16 B per env = 64 B */
 #define SPL_DECK_STRIDE 96 /* bytes per env of deck order (90 used: tier1[40] tier2[30] tier3[20]) */
@@ -123,6 +124,12 @@ typedef struct spl_step_io {
 	                                  the sampler's counter between replays) */
 	int32_t autoreset; /* same-step auto-reset (ppo_splendor.py:245-250) */
 	int32_t reserved_;
+	/* policy-ready observation formats (spl_step only; `obs` must then be NULL and auto-reset needs SPL_SHUFFLE_PHILOX).
+	 * The reference's caller casts the int32 observation to float for the MLP (ppo_splendor.py:221); here the cast is
+	 * fused into the step kernel: */
+	void *obs_f16;   /* [n][SPL_OBS_F16_PITCH] fp16, nullable: entries 0..296 = the observation (exact: all < 256),
+	                    297..303 = 0, so that a row is 16-byte aligned and the first Linear has K % 8 == 0 */
+	uint8_t *obs_u8; /* [n][297] nullable: the same observation as bytes (compact rollout buffers) */
 } spl_step_io_t;
 
 /* Upload the card / noble / token-return tables to the current device. Idempotent. */
@@ -155,6 +162,8 @@ int spl_rollout_plan(int64_t n, int32_t steps, int32_t *out);
 /* encode_observation (engine/encode.py:124-187) + legal_moves (engine/rules.py:40-93) of the current
  * states, without stepping (mask is all-zero for terminal states, as in envs/splendor_env.py:81). */
 int spl_observe(const spl_envs_t *envs, int32_t *obs, int8_t *mask, void *stream);
+/* the same with the policy-ready formats of spl_step_io (obs_f16 [n][SPL_OBS_F16_PITCH] fp16 and / or obs_u8 [n][297]) */
+int spl_observe_policy(const spl_envs_t *envs, void *obs_f16, uint8_t *obs_u8, int8_t *mask, void *stream);
 
 /* random_opponent (wrappers/selfplay.py:66-73) batched: uniform over the legal actions of mask[n][45],
  * a = k-th set bit with k = philox4x32-10(key, ctr=(global env, t)).x mod popcount; 0 if none legal. */

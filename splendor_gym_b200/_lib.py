@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("SPL_LIB") or os.path.join(HERE, "libsplendor_b200.so"
 
 NUM_ACTIONS = 45
 OBS_DIM = 297
+OBS_F16_PITCH = 304
 ROW_LEN = 166
 STATE_PLANES = 4
 DECK_STRIDE = 96
@@ -36,7 +37,7 @@ EXPORTS = (
     "spl_init", "spl_reset", "spl_step", "spl_observe", "spl_random_action", "spl_export_state", "spl_import_state",
     "spl_dual_combine", "spl_error_string", "spl_version", "spl_host_ret_table", "spl_launch_count",
     "spl_timing_enable", "spl_timing_read", "spl_rollout_random", "spl_scripted_action", "spl_masked_sample", "spl_gae",
-    "spl_host_create", "spl_host_destroy", "spl_host_step", "spl_host_observe", "spl_host_set_threads", "spl_host_expand", "spl_rollout_plan",
+    "spl_host_create", "spl_host_destroy", "spl_host_step", "spl_host_observe", "spl_host_set_threads", "spl_host_expand", "spl_rollout_plan", "spl_observe_policy",
 )
 
 BOT_RANDOM, BOT_GREEDY_V1, BOT_BASIC_PRIORITY, BOT_GREEDY_V2 = 0, 1, 2, 3
@@ -60,6 +61,7 @@ class SplStepIO(C.Structure):
         ("reward", C.c_void_p), ("terminated", C.c_void_p), ("info", C.c_void_p), ("stats", C.c_void_p),
         ("next_action", C.c_void_p), ("action_key", C.c_uint64), ("action_t", C.c_uint64),
         ("action_t_base", C.c_void_p), ("autoreset", C.c_int32), ("reserved_", C.c_int32),
+        ("obs_f16", C.c_void_p), ("obs_u8", C.c_void_p),
     ]
 
 
@@ -109,6 +111,8 @@ def load():
     L.spl_gae.argtypes = [vp, vp, vp, vp, C.c_int32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.spl_observe.restype = C.c_int
     L.spl_observe.argtypes = [C.POINTER(SplEnvs), vp, vp, vp]
+    L.spl_observe_policy.restype = C.c_int
+    L.spl_observe_policy.argtypes = [C.POINTER(SplEnvs), vp, vp, vp, vp]
     L.spl_random_action.restype = C.c_int
     L.spl_random_action.argtypes = [vp, i64, u64, u64, u64, vp, vp]
     L.spl_export_state.restype = C.c_int

@@ -10,6 +10,7 @@
 //   * mask    : 45-bit ballot-style bitset per lane, exchanged by shuffle and expanded to the contiguous
 //               [32 x 45] int8 tile as 90 int4 stores
 // No tensor cores: the path is integer/branch logic bounded by HBM writes (1,370 B per env-step).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -155,6 +156,42 @@ __device__ __forceinline__ void spl_store_obs_tile_u8(uint8_t* gtile, const uint
 	}
 }
 
+// Policy-ready observation tile: fp16 [32][SPL_OBS_F16_PITCH] (the 297 entries + 7 zero columns, so that a row is 608
+// bytes = 38 int4 and the first Linear of the policy sees a K that is a multiple of 8 -- K = 297 sends a half-precision
+// GEMM down a misaligned slow path, 7x slower on B200).  Every entry is an integer < 256, exact in fp16: two bytes are
+// merged with 0x64 into the fp16 pair (1024 + b0, 1024 + b1) by one PRMT and 1024 is subtracted by one HSUB2.
+__device__ __forceinline__ uint32_t spl_bytes_to_half2(uint32_t v, uint32_t sel) {
+	const uint32_t x = __byte_perm(v, 0x64646464u, sel), k = 0x64006400u;
+	const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&x), *reinterpret_cast<const __half2*>(&k));
+	return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void spl_store_obs_tile_f16(__half* gtile, const uint32_t* tile, int lane, int rows, bool vec) {
+	constexpr int ROW4 = SPL_OBS_F16_PITCH / 8;  // int4 per row
+	if (rows == 32 && vec) {
+		int4* g4 = reinterpret_cast<int4*>(gtile);
+#pragma unroll 2
+		for (int q = lane; q < 32 * ROW4; q += 32) {
+			const int r = q / ROW4, j = q - r * ROW4;
+			const int b = SPL_OBS_DIM * r + 8 * j;  // first source byte in the flat byte tile
+			const uint32_t* w = tile + (b >> 2);
+			const bool last = j == ROW4 - 1;        // columns 296..303: one entry + the zero padding
+			const uint32_t w0 = w[0], w1 = last ? 0u : w[1], w2 = last ? 0u : w[2];
+			const uint32_t sh = 8u * (uint32_t)(b & 3);
+			uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+			if (last) lo &= 0xFFu;
+			__stcs(g4 + q, make_int4((int)spl_bytes_to_half2(lo, 0x5140), (int)spl_bytes_to_half2(lo, 0x7362),
+			                         (int)spl_bytes_to_half2(hi, 0x5140), (int)spl_bytes_to_half2(hi, 0x7362)));
+		}
+	} else {
+		const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+		for (int e = lane; e < rows * SPL_OBS_F16_PITCH; e += 32) {
+			const int r = e / SPL_OBS_F16_PITCH, c = e - r * SPL_OBS_F16_PITCH;
+			gtile[e] = __ushort2half_rn(c < SPL_OBS_DIM ? (unsigned short)tb[SPL_OBS_DIM * r + c] : (unsigned short)0);
+		}
+	}
+}
+
 // reward of envs/splendor_env.py:61-80 as a small code (the host path moves one byte, not a float)
 __device__ __forceinline__ uint32_t spl_reward_code(float r) {
 	return r == 0.0f ? SPL_REWARD_CODE_ZERO : r == 1.0f ? SPL_REWARD_CODE_WIN : r == -1.0f ? SPL_REWARD_CODE_LOSS
@@ -272,6 +309,7 @@ struct StepParams {
 	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
 	int sync;    // rollout kernel: CTA barrier per lock-step (keeps the warps of a CTA in the same code region)
 	uint8_t* obs_u8;  // compact outputs (host path, spl_host.cu): observation tile as bytes [n][297] ...
+	__half* obs_f16;  // policy-ready observation, fp16 [n][SPL_OBS_F16_PITCH] (F16 output mode; obs_u8 may accompany it)
 	uint4* side;      // ... and one 16-byte record per env: legal-mask bits, reward code, terminated, info, sampled action
 	int chunk, nchunks;  // rollout kernel: lock-steps per work unit, chunks per tile group (spl_chunk_bounds)
 };
@@ -398,8 +436,13 @@ __device__ __forceinline__ const SplTables* spl_stage_tables(SplTables* T) {
 // COMPACT (host path): outputs are the uint8 observation tile + one 16-byte record per env instead of the
 // reference-typed int32 / int8 / float arrays -- 313 B instead of 1,243 B per env-step cross PCIe and the host
 // widens them (spl_host_expand.cpp).
-template <bool DO_STEP, int WPC, bool COMPACT>
+//   OUT = SPL_OUT_I32 reference-typed int32 observation | SPL_OUT_COMPACT | SPL_OUT_F16 (fp16 policy input and / or bytes)
+#define SPL_OUT_I32 0
+#define SPL_OUT_COMPACT 1
+#define SPL_OUT_F16 2
+template <bool DO_STEP, int WPC, int OUT>
 __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) {
+	constexpr bool COMPACT = OUT == SPL_OUT_COMPACT;
 	__shared__ SplTables Ts;
 	__shared__ __align__(16) uint32_t tiles[WPC][SPL_TILE_WORDS];
 	SplTile tl;
@@ -446,7 +489,16 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 				__stcs(p.side + env, make_uint4((uint32_t)m, (uint32_t)(m >> 32) | (spl_reward_code(r.reward) << 16) | ((uint32_t)r.terminated << 24),
 				                               (uint32_t)r.info | ((uint32_t)sampled << 8), 0u));
 		} else {
-			spl_tile_emit(p, tl, s, w, env, valid, p.obs, p.mask, p.next_action, t, m);
+			spl_tile_emit(p, tl, s, w, env, valid, OUT == SPL_OUT_F16 ? nullptr : p.obs, p.mask, p.next_action, t, m);
+			if (OUT == SPL_OUT_F16) {
+				SplObsStager stage(tl.smem, tl.lane, w[0]);
+				spl_encode_observation(w, s, tl.T, stage);
+				__syncwarp();
+				if (p.obs_f16 != nullptr)
+					spl_store_obs_tile_f16(p.obs_f16 + tl.ti * 32 * SPL_OBS_F16_PITCH, tl.smem, tl.lane, tl.rows, p.vec_ok);
+				if (p.obs_u8 != nullptr) spl_store_obs_tile_u8(p.obs_u8 + tl.ti * 32 * SPL_OBS_DIM, tl.smem, tl.lane, tl.rows, p.vec_ok);
+				__syncwarp();
+			}
 		}
 	}
 }
@@ -956,10 +1008,12 @@ int spl_init(void) {
 	SPL_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
 	SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_occ[kid][slot], K, threads, 0));                       \
 	if (g_occ[kid][slot] < 1) g_occ[kid][slot] = 1;
-	SPL_SETUP((spl_step_kernel<true, 4, false>), 0, 1, 128)
-	SPL_SETUP((spl_step_kernel<false, 4, false>), 1, 1, 128)
-	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_SETUP((spl_step_kernel<true, 4, SPL_OUT_I32>), 0, 1, 128)
+	SPL_SETUP((spl_step_kernel<false, 4, SPL_OUT_I32>), 1, 1, 128)
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true, 4, SPL_OUT_COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false, 4, SPL_OUT_COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true, 4, SPL_OUT_F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false, 4, SPL_OUT_F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	SPL_SETUP((spl_rollout_kernel<1>), 2, 0, 32)
 	SPL_SETUP((spl_rollout_kernel<4>), 2, 1, 128)
 #undef SPL_SETUP
@@ -1026,7 +1080,7 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.steps = 1;
 	p.sync = 0;
 	p.chunk = 1, p.nchunks = 1;
-	p.obs_u8 = nullptr, p.side = nullptr;
+	p.obs_u8 = nullptr, p.side = nullptr, p.obs_f16 = nullptr;
 }
 
 // Launch shape.  Single-step kernels: 4-warp CTAs, persistent over tiles (the 2 KB table staging is paid per
@@ -1071,14 +1125,24 @@ static LaunchShape launch_shape(int64_t n, int kernel) {
 	return L;
 }
 
-static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, int32_t* obs, int8_t* mask, cudaStream_t st) {
+static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, int32_t* obs, int8_t* mask, cudaStream_t st,
+                       void* obs_f16 = nullptr, uint8_t* obs_u8 = nullptr) {
 	StepParams p;
 	fill_step_params(p, e, io, obs, mask);
+	const bool f16 = obs_f16 != nullptr || obs_u8 != nullptr;
+	if (f16) {
+		if (obs != nullptr) return SPL_E_BADARG;  // one observation format per call
+		p.obs_f16 = (__half*)obs_f16, p.obs_u8 = obs_u8;
+		p.vec_ok = (((uintptr_t)obs_f16 | (uintptr_t)obs_u8 | (uintptr_t)mask) & 15) == 0;
+	}
 	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
-	if (do_step) spl_step_kernel<true, 4, false><<<L.grid, 128, 0, st>>>(p);
-	else spl_step_kernel<false, 4, false><<<L.grid, 128, 0, st>>>(p);
+	if (f16) {
+		if (do_step) spl_step_kernel<true, 4, SPL_OUT_F16><<<L.grid, 128, 0, st>>>(p);
+		else spl_step_kernel<false, 4, SPL_OUT_F16><<<L.grid, 128, 0, st>>>(p);
+	} else if (do_step) spl_step_kernel<true, 4, SPL_OUT_I32><<<L.grid, 128, 0, st>>>(p);
+	else spl_step_kernel<false, 4, SPL_OUT_I32><<<L.grid, 128, 0, st>>>(p);
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
 	g_launches++;
 	return (int)cudaGetLastError();
@@ -1098,8 +1162,8 @@ int spl_launch_compact(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
-	if (do_step) spl_step_kernel<true, 4, true><<<L.grid, 128, 0, st>>>(p);
-	else spl_step_kernel<false, 4, true><<<L.grid, 128, 0, st>>>(p);
+	if (do_step) spl_step_kernel<true, 4, SPL_OUT_COMPACT><<<L.grid, 128, 0, st>>>(p);
+	else spl_step_kernel<false, 4, SPL_OUT_COMPACT><<<L.grid, 128, 0, st>>>(p);
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
 	g_launches++;
 	return (int)cudaGetLastError();
@@ -1116,7 +1180,8 @@ int spl_step(const spl_envs_t* envs, const spl_step_io_t* io, void* stream) {
 	// 624-word generator state per env, so finished envs are queued for the reset kernel that follows
 	const bool worklist = io->autoreset && envs->shuffle_mode != SPL_SHUFFLE_PHILOX;
 	if (worklist) SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, 16, st));
-	rc = launch_step(envs, io, true, io->obs, io->mask, st);
+	if ((io->obs_f16 || io->obs_u8) && worklist) return SPL_E_BADARG;  // the MT19937 reset kernel writes int32 observations only
+	rc = launch_step(envs, io, true, io->obs, io->mask, st, io->obs_f16, io->obs_u8);
 	if (rc) return rc;
 	if (worklist) {
 		// the reset kernel also re-samples next_action for the envs whose mask it replaces
@@ -1169,6 +1234,13 @@ int spl_observe(const spl_envs_t* envs, int32_t* obs, int8_t* mask, void* stream
 	int rc = check_envs(envs);
 	if (rc) return rc;
 	return launch_step(envs, nullptr, false, obs, mask, (cudaStream_t)stream);
+}
+
+int spl_observe_policy(const spl_envs_t* envs, void* obs_f16, uint8_t* obs_u8, int8_t* mask, void* stream) {
+	int rc = check_envs(envs);
+	if (rc) return rc;
+	if (!obs_f16 && !obs_u8) return SPL_E_BADARG;
+	return launch_step(envs, nullptr, false, nullptr, mask, (cudaStream_t)stream, obs_f16, obs_u8);
 }
 
 int spl_random_action(const int8_t* mask, int64_t n, uint64_t env_offset, uint64_t key, uint64_t t, int32_t* actions, void* stream) {

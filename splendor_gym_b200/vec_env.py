@@ -66,13 +66,17 @@ class SplendorVecEnv:
     env_offset : global index of env 0 (multi-GPU sharding; results do not depend on the GPU count).
     autoreset : same-step auto-reset as in ppo_splendor.py:245-250 (reward/terminated of the finished
         episode, observation/mask of the new one).
+    obs_format : ``"int32"`` = the reference's observation dtype (envs/splendor_env.py:34-36).  ``"f16"`` = policy-ready:
+        ``self.obs_f16`` is an fp16 ``[N, 304]`` tensor (entries 0..296 = the observation, exact; 297..303 = 0) that an MLP
+        consumes without the cast of ppo_splendor.py:221 and with a 16-byte-aligned K, and ``self.obs`` holds the same
+        values as ``uint8 [N, 297]`` (rollout buffers a quarter of the size).  Needs ``shuffle="philox"`` for auto-reset.
     """
 
     num_actions = L.NUM_ACTIONS
     obs_dim = L.OBS_DIM
 
     def __init__(self, num_envs: int, device="cuda", seed: int = 0, shuffle: str = "philox", env_offset: int = 0,
-                 autoreset: bool = True):
+                 autoreset: bool = True, obs_format: str = "int32"):
         if num_envs <= 0:
             raise ValueError("num_envs must be positive")
         self.lib = L.load()
@@ -92,7 +96,17 @@ class SplendorVecEnv:
         self.decks = torch.zeros((n, L.DECK_STRIDE), dtype=torch.uint8, device=d)
         self.episode = torch.zeros(n, dtype=torch.int32, device=d)
         self.scratch = torch.zeros(n + 4, dtype=torch.int32, device=d)
-        self.obs = torch.zeros((n, L.OBS_DIM), dtype=torch.int32, device=d)
+        if obs_format not in ("int32", "f16"):
+            raise ValueError("obs_format must be 'int32' or 'f16'")
+        self.obs_format = obs_format
+        if obs_format == "f16":
+            if self.autoreset and self.shuffle_mode != L.SHUFFLE_PHILOX:
+                raise L.SplendorB200Error("obs_format='f16' with auto-reset needs shuffle='philox'")
+            self.obs = torch.zeros((n, L.OBS_DIM), dtype=torch.uint8, device=d)
+            self.obs_f16 = torch.zeros((n, L.OBS_F16_PITCH), dtype=torch.float16, device=d)
+        else:
+            self.obs = torch.zeros((n, L.OBS_DIM), dtype=torch.int32, device=d)
+            self.obs_f16 = None
         self.mask = torch.zeros((n, L.NUM_ACTIONS), dtype=torch.int8, device=d)
         self.reward = torch.zeros(n, dtype=torch.float32, device=d)
         self._terminated = torch.zeros(n, dtype=torch.uint8, device=d)
@@ -159,9 +173,13 @@ class SplendorVecEnv:
             seeds = seeds.to(device=self.device, dtype=torch.int64).contiguous()
         if reset_mask is not None:
             reset_mask = reset_mask.to(device=self.device).view(-1).to(torch.uint8).contiguous()
+        f16 = self.obs_format == "f16"
         with torch.cuda.device(self.device):
-            L.check(self.lib.spl_reset(C.byref(self._envs), _ptr(seeds), _ptr(reset_mask), self.obs.data_ptr(),
-                                       self.mask.data_ptr(), self._stream()), "spl_reset")
+            L.check(self.lib.spl_reset(C.byref(self._envs), _ptr(seeds), _ptr(reset_mask), None if f16 else self.obs.data_ptr(),
+                                       None if f16 else self.mask.data_ptr(), self._stream()), "spl_reset")
+            if f16:
+                L.check(self.lib.spl_observe_policy(C.byref(self._envs), self.obs_f16.data_ptr(), self.obs.data_ptr(),
+                                                    self.mask.data_ptr(), self._stream()), "spl_observe_policy")
         if reset_mask is None:
             self._t = 0
         self._is_reset = True
@@ -170,7 +188,7 @@ class SplendorVecEnv:
     def step(self, actions: torch.Tensor, *, active: Optional[torch.Tensor] = None, out_obs: Optional[torch.Tensor] = None,
              out_mask: Optional[torch.Tensor] = None, sample_next: bool = False, autoreset: Optional[bool] = None,
              out_reward: Optional[torch.Tensor] = None, out_terminated: Optional[torch.Tensor] = None,
-             out_next_action: Optional[torch.Tensor] = None, write_obs: bool = True):
+             out_next_action: Optional[torch.Tensor] = None, write_obs: bool = True, out_obs_f16: Optional[torch.Tensor] = None):
         """``SplendorEnv.step`` for every env in lock-step -> (obs, reward, terminated, truncated, info).
 
         ``out_obs`` / ``out_mask`` redirect the observation / mask of this step into caller storage (e.g. a
@@ -189,7 +207,13 @@ class SplendorVecEnv:
         reward = self.reward if out_reward is None else out_reward
         term = self._terminated if out_terminated is None else out_terminated
         nxt = self.next_action if out_next_action is None else out_next_action
-        io.obs, io.mask = (obs.data_ptr() if write_obs else None), mask.data_ptr()
+        if self.obs_format == "f16":  # fp16 policy input + byte observation instead of the int32 array
+            f16 = self.obs_f16 if out_obs_f16 is None else out_obs_f16
+            io.obs, io.mask = None, mask.data_ptr()
+            io.obs_f16, io.obs_u8 = (f16.data_ptr() if write_obs else None), (obs.data_ptr() if write_obs else None)
+        else:
+            io.obs, io.mask = (obs.data_ptr() if write_obs else None), mask.data_ptr()
+            io.obs_f16, io.obs_u8 = None, None
         io.reward, io.terminated, io.info = reward.data_ptr(), term.data_ptr(), self.info_bits.data_ptr()
         io.stats = self.stats.data_ptr()
         io.next_action = nxt.data_ptr() if (sample_next or out_next_action is not None) else None
@@ -218,6 +242,7 @@ class SplendorVecEnv:
         assert reward.numel() == steps * n and terminated.numel() == steps * n
         io = self._io
         io.actions, io.active = actions.data_ptr(), None
+        io.obs_f16, io.obs_u8 = None, None
         io.obs, io.mask = _ptr(obs), _ptr(mask)
         io.reward, io.terminated, io.info = reward.data_ptr(), terminated.data_ptr(), _ptr(info)
         io.stats = self.stats.data_ptr()
@@ -315,7 +340,11 @@ class SplendorVecEnv:
         obs = self.obs if out_obs is None else out_obs
         mask = self.mask if out_mask is None else out_mask
         with torch.cuda.device(self.device):
-            L.check(self.lib.spl_observe(C.byref(self._envs), obs.data_ptr(), mask.data_ptr(), self._stream()), "spl_observe")
+            if self.obs_format == "f16":
+                L.check(self.lib.spl_observe_policy(C.byref(self._envs), self.obs_f16.data_ptr(), obs.data_ptr(), mask.data_ptr(),
+                                                    self._stream()), "spl_observe_policy")
+            else:
+                L.check(self.lib.spl_observe(C.byref(self._envs), obs.data_ptr(), mask.data_ptr(), self._stream()), "spl_observe")
         return obs, mask
 
     def sample_random_actions(self, mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

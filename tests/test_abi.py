@@ -44,13 +44,14 @@ def test_struct_layouts_match_header():
 
     # struct spl_envs: 4 pointers, 2 int64, 2 uint64, 2 int32 ; struct spl_step_io: 9 pointers, 2 uint64, 1 pointer, 2 int32
     assert C.sizeof(_lib.SplEnvs) == 4 * 8 + 4 * 8 + 8
-    assert C.sizeof(_lib.SplStepIO) == 9 * 8 + 2 * 8 + 8 + 8
+    assert C.sizeof(_lib.SplStepIO) == 9 * 8 + 2 * 8 + 8 + 8 + 2 * 8 and _lib.SplStepIO.obs_f16.offset == 104
     assert _lib.SplEnvs.shuffle_mode.offset == 64 and _lib.SplStepIO.autoreset.offset == 96
     # struct spl_host_io: 9 pointers, 2 uint64, 2 int32
     assert C.sizeof(_lib.SplHostIO) == 9 * 8 + 2 * 8 + 8 and _lib.SplHostIO.autoreset.offset == 88
     text = open(os.path.join(ROOT, "include", "splendor_b200.h")).read()
     for name, val in (("SPL_NUM_ACTIONS", _lib.NUM_ACTIONS), ("SPL_OBS_DIM", _lib.OBS_DIM), ("SPL_ROW_LEN", _lib.ROW_LEN),
-                      ("SPL_DECK_STRIDE", _lib.DECK_STRIDE), ("SPL_RET_TABLE_LEN", _lib.RET_TABLE_LEN)):
+                      ("SPL_DECK_STRIDE", _lib.DECK_STRIDE), ("SPL_RET_TABLE_LEN", _lib.RET_TABLE_LEN),
+                      ("SPL_OBS_F16_PITCH", _lib.OBS_F16_PITCH)):
         assert re.search(rf"#define {name} {val}\b", text), name
     for name, val in (("SPL_INFO_ILLEGAL", _lib.INFO_ILLEGAL), ("SPL_INFO_NOLEGAL_DRAW", _lib.INFO_NOLEGAL_DRAW),
                       ("SPL_INFO_TURN_LIMIT", _lib.INFO_TURN_LIMIT), ("SPL_INFO_TERMINATED", _lib.INFO_TERMINATED),

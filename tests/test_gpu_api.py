@@ -346,3 +346,85 @@ def test_step_host_rejects_what_it_cannot_do():
     assert o.shape == (64, 297)
     with pytest.raises(ValueError):
         e.step_host(np.zeros(3, np.int32), autoreset=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [33, 1000, 4096])
+def test_f16_observation_mode_equals_int32(n):
+    """obs_format='f16' (fp16 [N,304] policy input + uint8 observation, cast fused into the step kernel) carries exactly
+    the values of the reference-typed int32 observation; masks, rewards, terminations, info and state are unchanged."""
+    import torch
+    from splendor_gym_b200 import SplendorVecEnv
+
+    a = SplendorVecEnv(n, seed=9, shuffle="philox", autoreset=True)
+    b = SplendorVecEnv(n, seed=9, shuffle="philox", autoreset=True, obs_format="f16")
+    oa, _ = a.reset()
+    ob, _ = b.reset()
+
+    def check(t):
+        assert b.obs.dtype == torch.uint8 and b.obs_f16.dtype == torch.float16 and b.obs_f16.shape == (n, 304)
+        assert torch.equal(a.obs, b.obs.to(torch.int32)), f"step {t}: uint8 obs"
+        assert torch.equal(a.obs.to(torch.float16), b.obs_f16[:, :297]), f"step {t}: fp16 obs"
+        assert not b.obs_f16[:, 297:].any(), f"step {t}: padding columns"
+        assert torch.equal(a.mask, b.mask)
+
+    check(-1)
+    act = a.sample_random_actions().clone()
+    for t in range(90):
+        if t % 11 == 5:
+            act[::37] = 44 - act[::37]  # mostly illegal
+        a.step(act, sample_next=True)
+        b.step(act, sample_next=True)
+        check(t)
+        assert torch.equal(a.reward, b.reward) and torch.equal(a._terminated, b._terminated) and torch.equal(a.info_bits, b.info_bits)
+        assert torch.equal(a.next_action, b.next_action)
+        act = a.next_action.clone()
+    assert torch.equal(a.export_state(), b.export_state()) and torch.equal(a.stats, b.stats)
+    # redirected outputs (rollout-buffer slices) and observe()
+    buf8 = torch.zeros((n, 297), dtype=torch.uint8, device="cuda")
+    buf16 = torch.zeros((n, 304), dtype=torch.float16, device="cuda")
+    a.step(act)
+    b.step(act, out_obs=buf8, out_obs_f16=buf16)
+    assert torch.equal(a.obs, buf8.to(torch.int32)) and torch.equal(a.obs.to(torch.float16), buf16[:, :297])
+    b.observe()
+    assert torch.equal(a.obs, b.obs.to(torch.int32)) and torch.equal(a.obs.to(torch.float16), b.obs_f16[:, :297])
+
+
+@pytest.mark.gpu
+def test_f16_mode_argument_checks():
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200._lib import SplendorB200Error
+
+    with pytest.raises(SplendorB200Error):
+        SplendorVecEnv(64, shuffle="mt19937", autoreset=True, obs_format="f16")
+    with pytest.raises(ValueError):
+        SplendorVecEnv(64, obs_format="bf16")
+    e = SplendorVecEnv(64, seed=3, shuffle="mt19937", autoreset=False, obs_format="f16")  # fine without auto-reset
+    e.reset()
+    e.step(e.sample_random_actions())
+    assert e.obs_f16[:, :297].max() < 256
+
+
+@pytest.mark.gpu
+def test_ppo_rollout_f16_policy_input_matches_cast_path():
+    """The fp16 policy input emitted by the step kernel + zero-padded first / last layers give the same logits as the reference's
+    cast path (obs.to(fp16) through the unpadded network) -- same fp16 GEMM inputs, so the same action choices."""
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200.scripts.ppo_rollout import ActorCritic, collect, pad_first_layer, pad_head
+
+    torch.manual_seed(1)
+    net = ActorCritic().cuda().half().eval()
+    a = SplendorVecEnv(4096, seed=6, shuffle="philox", autoreset=True)
+    b = SplendorVecEnv(4096, seed=6, shuffle="philox", autoreset=True, obs_format="f16")
+    a.reset()
+    b.reset()
+    padded = pad_head(pad_first_layer(net.actor))
+    with torch.no_grad():
+        ref = net.actor(a.obs.to(torch.float16)).float()
+        got = padded(b.obs_f16)[:, :45].float()
+    assert torch.allclose(ref, got, atol=2e-3, rtol=2e-3)
+    net.actor, net.critic = padded, pad_first_layer(net.critic)
+    buf = collect(b, net, 48, dtype=torch.float16)
+    assert buf["obs"].dtype == torch.uint8
+    legal = buf["masks"].gather(2, buf["actions"].long().unsqueeze(2)).squeeze(2)
+    assert bool((legal[buf["masks"].sum(dim=2) > 0] == 1).all()) and int(buf["terminals"].sum()) > 50
