@@ -8,6 +8,7 @@
 // bits->bytes table for the mask.
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <omp.h>
@@ -57,6 +58,34 @@ __attribute__((target("avx2"))) void widen_avx2(const uint8_t* src, int32_t* dst
 	for (; i < n; i++) dst[i] = (int32_t)src[i];
 	_mm_sfence();
 }
+__attribute__((target("avx512f"))) void widen_avx512(const uint8_t* src, int32_t* dst, size_t n) {
+	size_t i = 0;
+	while (i < n && ((uintptr_t)(dst + i) & 63)) {  // head: 64-byte boundary, then one full cache line per streaming store
+		dst[i] = (int32_t)src[i];
+		i++;
+	}
+	for (; i + 64 <= n; i += 64) {
+		const __m128i a = _mm_loadu_si128((const __m128i*)(src + i));
+		const __m128i b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+		const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32));
+		const __m128i d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+		_mm512_stream_si512((__m512i*)(dst + i), _mm512_cvtepu8_epi32(a));
+		_mm512_stream_si512((__m512i*)(dst + i + 16), _mm512_cvtepu8_epi32(b));
+		_mm512_stream_si512((__m512i*)(dst + i + 32), _mm512_cvtepu8_epi32(c));
+		_mm512_stream_si512((__m512i*)(dst + i + 48), _mm512_cvtepu8_epi32(d));
+	}
+	for (; i < n; i++) dst[i] = (int32_t)src[i];
+	_mm_sfence();
+}
+int simd_level() {  // 0 scalar, 2 AVX2, 5 AVX-512 (SPL_HOST_SIMD overrides downwards)
+	static const int v = [] {
+		int lvl = __builtin_cpu_supports("avx512f") ? 5 : (__builtin_cpu_supports("avx2") ? 2 : 0);
+		const char* e = getenv("SPL_HOST_SIMD");
+		if (e && atoi(e) < lvl) lvl = atoi(e);
+		return lvl;
+	}();
+	return v;
+}
 bool have_avx2() {
 	static const bool v = __builtin_cpu_supports("avx2");
 	return v;
@@ -65,7 +94,8 @@ bool have_avx2() {
 
 inline void widen(const uint8_t* src, int32_t* dst, size_t n) {
 #if defined(__x86_64__)
-	if (have_avx2()) return widen_avx2(src, dst, n);
+	if (simd_level() >= 5) return widen_avx512(src, dst, n);
+	if (simd_level() >= 2) return widen_avx2(src, dst, n);
 #endif
 	widen_scalar(src, dst, n);
 }
