@@ -643,39 +643,69 @@ struct ResetParams {
 	const uint64_t* action_t_base;
 };
 
-struct SplMT {  // MT19937 state of one lane, lane-interleaved in shared memory (conflict-free)
+// MT19937 state of one lane, lane-interleaved in shared memory (conflict-free).  The generator sits on the critical
+// path of every bit-exact auto-reset, and one lane cannot go faster than its dependent chain, so that chain is kept as
+// short as it can be:
+//   * random.Random(a) = init_genrand(19650218) + init_by_array(key): the init_genrand recurrence is carried in a
+//     register next to the first init_by_array pass (624 fused iterations, one store each, no loads); the second pass
+//     carries mt[i-1] in a register and only loads the old mt[i], whose address does not depend on the chain;
+//   * the first 227 outputs depend on OLD state words only (k, k+1, k+397), so they are produced on demand without the
+//     624-word regeneration; a deal consumes ~130 outputs.  Output 228 (never seen in 1e6 games, but reachable through
+//     rejection sampling) triggers the regular in-place regeneration of the untouched state.
+#ifndef SPL_MT_LAZY
+#define SPL_MT_LAZY 227 /* a smaller value is still exact (tests build one to exercise the regeneration path) */
+#endif
+struct SplMT {
 	uint32_t* mt;
 	int idx;
+	bool twisted;
 	__device__ __forceinline__ uint32_t& at(int i) { return mt[i * 32]; }
 	__device__ void seed(uint64_t a) {  // random.Random(a): init_by_array over the 32-bit words of a
-		uint32_t key[2] = {(uint32_t)a, (uint32_t)(a >> 32)};
-		int klen = key[1] ? 2 : 1;
-		at(0) = 19650218u;
-		for (int i = 1; i < 624; i++) at(i) = 1812433253u * (at(i - 1) ^ (at(i - 1) >> 30)) + (uint32_t)i;
-		int i = 1, j = 0;
-		for (int k = 624; k; k--) {
-			at(i) = (at(i) ^ ((at(i - 1) ^ (at(i - 1) >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
-			i++, j++;
-			if (i >= 624) at(0) = at(623), i = 1;
-			if (j >= klen) j = 0;
+		const uint32_t key0 = (uint32_t)a, key1 = (uint32_t)(a >> 32);
+		const bool two = key1 != 0;
+		uint32_t g = 19650218u, q = g, m1_1 = 0, j = 0;
+#pragma unroll 4
+		for (int i = 1; i < 624; i++) {  // init_genrand (g) and iterations 1..623 of the first init_by_array loop (q)
+			g = 1812433253u * (g ^ (g >> 30)) + (uint32_t)i;
+			q = (g ^ ((q ^ (q >> 30)) * 1664525u)) + (j ? key1 : key0) + j;
+			at(i) = q;
+			if (i == 1) m1_1 = q;
+			j = two ? (j ^ 1u) : 0u;
 		}
-		for (int k = 623; k; k--) {
-			at(i) = (at(i) ^ ((at(i - 1) ^ (at(i - 1) >> 30)) * 1566083941u)) - (uint32_t)i;
-			i++;
-			if (i >= 624) at(0) = at(623), i = 1;
+		// 624th iteration: the index wrapped (mt[0] <- mt[623] = q) and mt[1] is updated once more
+		uint32_t p = (m1_1 ^ ((q ^ (q >> 30)) * 1664525u)) + (j ? key1 : key0) + j;
+		const uint32_t m1p_1 = p;
+#pragma unroll 4
+		for (int i = 2; i < 624; i++) {  // second loop, iterations 1..622
+			p = (at(i) ^ ((p ^ (p >> 30)) * 1566083941u)) - (uint32_t)i;
+			at(i) = p;
 		}
+		// 623rd iteration after the wrap (mt[0] <- mt[623] = p): mt[1]; then mt[0] = 0x80000000
+		at(1) = (m1p_1 ^ ((p ^ (p >> 30)) * 1566083941u)) - 1u;
 		at(0) = 0x80000000u;
-		idx = 624;
+		idx = 0;
+		twisted = false;
+	}
+	__device__ void twist() {
+		for (int kk = 0; kk < 624; kk++) {
+			uint32_t y = (at(kk) & 0x80000000u) | (at((kk + 1) % 624) & 0x7fffffffu);
+			at(kk) = at((kk + 397) % 624) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+		}
 	}
 	__device__ uint32_t next() {
-		if (idx >= 624) {
-			for (int kk = 0; kk < 624; kk++) {
-				uint32_t y = (at(kk) & 0x80000000u) | (at((kk + 1) % 624) & 0x7fffffffu);
-				at(kk) = at((kk + 397) % 624) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+		uint32_t y;
+		if (!twisted && idx < SPL_MT_LAZY) {
+			const uint32_t u = (at(idx) & 0x80000000u) | (at(idx + 1) & 0x7fffffffu);
+			y = at(idx + 397) ^ (u >> 1) ^ ((u & 1u) ? 0x9908b0dfu : 0u);
+			idx++;
+		} else {
+			if (!twisted || idx >= 624) {
+				twist();
+				if (twisted) idx = 0;
+				twisted = true;
 			}
-			idx = 0;
+			y = at(idx++);
 		}
-		uint32_t y = at(idx++);
 		y ^= y >> 11;
 		y ^= (y << 7) & 0x9d2c5680u;
 		y ^= (y << 15) & 0xefc60000u;
@@ -731,13 +761,23 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	{
 		const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
 		uint32_t* dst = reinterpret_cast<uint32_t*>(T);
-		for (int i = lane; i < (int)(sizeof(SplTables) / 4); i += 32) dst[i] = src[i];
+#pragma unroll
+		for (int i = 0; i < (int)(sizeof(SplTables) / 4 + 31) / 32; i++)  // all loads in flight before the first store
+			if (i * 32 + lane < (int)(sizeof(SplTables) / 4)) dst[i * 32 + lane] = src[i * 32 + lane];
 	}
 	__syncwarp();
 	const int64_t count = p.list ? (int64_t)p.list[0] : p.n;
-	for (int64_t g = blockIdx.x; g * 32 < count; g += gridDim.x) {
-		const int64_t item = g * 32 + lane;
-		const bool valid = item < count;
+	// A work list (auto-reset of the envs that just finished) is short and sits on the critical path of the lock-step:
+	// spread it over every warp of the grid -- `ipw` items per warp instead of 32 -- so that the serial parts (one
+	// lane's MT19937 chain, one scattered output row per iteration) run side by side on all SMs.
+	int ipw = 32;
+	if (p.list != nullptr) {
+		const int64_t per = (count + gridDim.x - 1) / gridDim.x;
+		ipw = per < 1 ? 1 : (per > 32 ? 32 : (int)per);
+	}
+	for (int64_t g = blockIdx.x; g * ipw < count; g += gridDim.x) {
+		const int64_t item = g * ipw + lane;
+		const bool valid = lane < ipw && item < count;
 		const int64_t env = valid ? (p.list ? (int64_t)p.list[4 + item] : item) : 0;
 		uint8_t* deck = decks_s + lane * SPL_DECK_SMEM;
 		SplState s;
@@ -789,10 +829,10 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 				p.next_action[env] = spl_sample_action(m, p.action_key, p.env_offset + (uint64_t)env, t);
 			}
 			if (p.mask != nullptr)
-			for (int r = 0; r < 32; r++) {
+			for (int r = 0; r < ipw; r++) {
 				int64_t e = __shfl_sync(SPL_FULL, env, r);
 				uint64_t mr = __shfl_sync(SPL_FULL, m, r);
-				if (g * 32 + r < count) {
+				if (g * ipw + r < count) {
 					p.mask[e * SPL_NUM_ACTIONS + lane] = (int8_t)((mr >> lane) & 1);
 					if (lane < SPL_NUM_ACTIONS - 32) p.mask[e * SPL_NUM_ACTIONS + 32 + lane] = (int8_t)((mr >> (32 + lane)) & 1);
 				}
@@ -803,9 +843,9 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 			spl_encode_observation(w, s, T, stage);
 			__syncwarp();
 			const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
-			for (int r = 0; r < 32; r++) {
+			for (int r = 0; r < ipw; r++) {
 				int64_t e = __shfl_sync(SPL_FULL, env, r);
-				if (g * 32 + r < count) {
+				if (g * ipw + r < count) {
 #pragma unroll
 					for (int c = lane; c < SPL_OBS_DIM; c += 32) p.obs[e * SPL_OBS_DIM + c] = (int32_t)tb[SPL_OBS_DIM * r + c];
 				}
