@@ -71,6 +71,8 @@ static void default_threads() {
 
 extern "C" {
 
+int spl_host_destroy(spl_host_t* h);
+
 int spl_host_create(int64_t n, int32_t chunks, spl_host_t** out) {
 	if (n <= 0 || !out) return SPL_E_BADARG;
 	if (chunks <= 0) {
@@ -87,23 +89,32 @@ int spl_host_create(int64_t n, int32_t chunks, spl_host_t** out) {
 	spl_host* h = (spl_host*)calloc(1, sizeof(spl_host));
 	if (!h) return SPL_E_BADARG;
 	h->n = n, h->chunks = chunks;
-	SPL_CUDA(cudaGetDevice(&h->device));
-	SPL_CUDA(cudaMalloc(&h->d_obs, (size_t)n * SPL_OBS_DIM_ + 16));
-	SPL_CUDA(cudaMalloc(&h->d_side, (size_t)n * 16));
-	SPL_CUDA(cudaMalloc(&h->d_act, (size_t)n * 4));
-	SPL_CUDA(cudaHostAlloc(&h->h_obs, (size_t)n * SPL_OBS_DIM_ + 16, cudaHostAllocDefault));
-	SPL_CUDA(cudaHostAlloc(&h->h_side, (size_t)n * 16, cudaHostAllocDefault));
-	SPL_CUDA(cudaHostAlloc(&h->h_act, (size_t)n * 4, cudaHostAllocDefault));
-	for (int c = 0; c < chunks; c++) SPL_CUDA(cudaEventCreateWithFlags(&h->ev[c], cudaEventDisableTiming));
+	cudaError_t e = cudaGetDevice(&h->device);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_obs, (size_t)n * SPL_OBS_DIM_ + 16);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_side, (size_t)n * 16);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_act, (size_t)n * 4);
+	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_obs, (size_t)n * SPL_OBS_DIM_ + 16, cudaHostAllocDefault);
+	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_side, (size_t)n * 16, cudaHostAllocDefault);
+	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_act, (size_t)n * 4, cudaHostAllocDefault);
+	for (int c = 0; c < chunks && e == cudaSuccess; c++) e = cudaEventCreateWithFlags(&h->ev[c], cudaEventDisableTiming);
+	if (e != cudaSuccess) {  // nothing half-built is handed out (spl_host_destroy skips what was never created)
+		spl_host_destroy(h);
+		return (int)e;
+	}
 	*out = h;
 	return 0;
 }
 
 int spl_host_destroy(spl_host_t* h) {
 	if (!h) return 0;
-	cudaFree(h->d_obs), cudaFree(h->d_side), cudaFree(h->d_act);
-	cudaFreeHost(h->h_obs), cudaFreeHost(h->h_side), cudaFreeHost(h->h_act);
-	for (int c = 0; c < h->chunks; c++) cudaEventDestroy(h->ev[c]);
+	if (h->d_obs) cudaFree(h->d_obs);
+	if (h->d_side) cudaFree(h->d_side);
+	if (h->d_act) cudaFree(h->d_act);
+	if (h->h_obs) cudaFreeHost(h->h_obs);
+	if (h->h_side) cudaFreeHost(h->h_side);
+	if (h->h_act) cudaFreeHost(h->h_act);
+	for (int c = 0; c < h->chunks; c++)
+		if (h->ev[c]) cudaEventDestroy(h->ev[c]);
 	free(h);
 	return 0;
 }
