@@ -424,10 +424,21 @@ __device__ __forceinline__ void spl_store_state(const StepParams& p, int64_t env
 		p.state[pl * p.stride + env] = make_uint4(w[4 * pl + 0], w[4 * pl + 1], w[4 * pl + 2], w[4 * pl + 3]);
 }
 
+// constant tables -> shared memory, once per CTA: 128-bit loads, all of a thread's loads in flight before its first
+// store (a dependent load/store pair per iteration cost a 1-warp CTA 16 global-latency round trips = 6 us)
+template <int THREADS>
 __device__ __forceinline__ const SplTables* spl_stage_tables(SplTables* T) {
-	const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
-	uint32_t* dst = reinterpret_cast<uint32_t*>(T);
-	for (int i = threadIdx.x; i < (int)(sizeof(SplTables) / 4); i += blockDim.x) dst[i] = src[i];
+	static_assert(sizeof(SplTables) % 16 == 0, "SplTables is copied as uint4");
+	constexpr int N4 = (int)(sizeof(SplTables) / 16), PER = (N4 + THREADS - 1) / THREADS;
+	const uint4* src = reinterpret_cast<const uint4*>(&g_tables);
+	uint4* dst = reinterpret_cast<uint4*>(T);
+	uint4 v[PER];
+#pragma unroll
+	for (int k = 0; k < PER; k++)
+		if (k * THREADS + (int)threadIdx.x < N4) v[k] = src[k * THREADS + threadIdx.x];
+#pragma unroll
+	for (int k = 0; k < PER; k++)
+		if (k * THREADS + (int)threadIdx.x < N4) dst[k * THREADS + threadIdx.x] = v[k];
 	__syncthreads();
 	return T;
 }
@@ -446,7 +457,7 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 	__shared__ SplTables Ts;
 	__shared__ __align__(16) uint32_t tiles[WPC][SPL_TILE_WORDS];
 	SplTile tl;
-	tl.T = spl_stage_tables(&Ts);
+	tl.T = spl_stage_tables<WPC * 32>(&Ts);
 	tl.lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	tl.smem = tiles[warp];
@@ -538,7 +549,7 @@ __global__ void __launch_bounds__(WPC * 32, 20 / WPC) spl_rollout_kernel(const S
 	__shared__ __align__(16) uint32_t tiles[WPC][SPL_TILE_WORDS];
 	__shared__ uint32_t s_unit;
 	SplTile tl;
-	tl.T = spl_stage_tables(&Ts);
+	tl.T = spl_stage_tables<WPC * 32>(&Ts);
 	tl.lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	tl.smem = tiles[warp];
@@ -758,14 +769,7 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	uint8_t* decks_s = smem + sizeof(SplTables) + SPL_TILE_WORDS * 4;
 	uint32_t* mt_s = reinterpret_cast<uint32_t*>(decks_s + 32 * SPL_DECK_SMEM);
 	const int lane = threadIdx.x;
-	{
-		const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_tables);
-		uint32_t* dst = reinterpret_cast<uint32_t*>(T);
-#pragma unroll
-		for (int i = 0; i < (int)(sizeof(SplTables) / 4 + 31) / 32; i++)  // all loads in flight before the first store
-			if (i * 32 + lane < (int)(sizeof(SplTables) / 4)) dst[i * 32 + lane] = src[i * 32 + lane];
-	}
-	__syncwarp();
+	spl_stage_tables<32>(T);
 	const int64_t count = p.list ? (int64_t)p.list[0] : p.n;
 	// A work list (auto-reset of the envs that just finished) is short and sits on the critical path of the lock-step:
 	// spread it over every warp of the grid -- `ipw` items per warp instead of 32 -- so that the serial parts (one
@@ -1050,6 +1054,12 @@ int spl_init(void) {
 	if (g_occ[kid][slot] < 1) g_occ[kid][slot] = 1;
 	SPL_SETUP((spl_step_kernel<true, 4, SPL_OUT_I32>), 0, 1, 128)
 	SPL_SETUP((spl_step_kernel<false, 4, SPL_OUT_I32>), 1, 1, 128)
+	SPL_SETUP((spl_step_kernel<true, 1, SPL_OUT_I32>), 0, 0, 32)
+	SPL_SETUP((spl_step_kernel<false, 1, SPL_OUT_I32>), 1, 0, 32)
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true, 1, SPL_OUT_COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false, 1, SPL_OUT_COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true, 1, SPL_OUT_F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false, 1, SPL_OUT_F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true, 4, SPL_OUT_COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false, 4, SPL_OUT_COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true, 4, SPL_OUT_F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1123,8 +1133,8 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.obs_u8 = nullptr, p.side = nullptr, p.obs_f16 = nullptr;
 }
 
-// Launch shape.  Single-step kernels: 4-warp CTAs, persistent over tiles (the 2 KB table staging is paid per
-// CTA per launch).  Rollout kernel: persistent CTAs pulling (tile group, step chunk) units from the work queue;
+// Launch shape.  Single-step kernels: one tile (1-warp CTA) per CTA, non-persistent (the 2 KB table staging is one
+// 128-bit load per lane x 4).  Rollout kernel: persistent CTAs pulling (tile group, step chunk) units from the work queue;
 // 1-warp CTAs when every tile can be resident at once (e.g. 65,536 envs = 2,048 tiles: one CTA per tile spreads
 // them evenly and the balancing comes from tiles migrating between SMs from chunk to chunk), 4-warp CTAs at full
 // occupancy otherwise.  Measured on B200 (tools/sweep_rollout.py): fewer CTAs than tile groups is slower (the
@@ -1143,7 +1153,7 @@ static LaunchShape launch_shape(int64_t n, int kernel) {
 	const int64_t ntiles = (n + 31) / 32;
 	LaunchShape L;
 	int64_t resident4 = (int64_t)g_num_sms * g_occ[kernel][1] * 4;
-	L.wpc = kernel != 2 ? 4 : env_int("SPL_WPC", ntiles <= resident4 ? 1 : 4);
+	L.wpc = kernel != 2 ? env_int("SPL_STEP_WPC", 1) : env_int("SPL_WPC", ntiles <= resident4 ? 1 : 4);
 	if (L.wpc != 1) L.wpc = 4;
 	int64_t ctas = (ntiles + L.wpc - 1) / L.wpc;
 	int64_t cap = (int64_t)g_num_sms * g_occ[kernel][L.wpc == 1 ? 0 : 1];
@@ -1165,6 +1175,19 @@ static LaunchShape launch_shape(int64_t n, int kernel) {
 	return L;
 }
 
+// single-step kernels: 1-warp CTAs by default (measured 3-7 % faster than 4-warp CTAs once the table staging is
+// vectorised: finer-grained balancing by the hardware CTA scheduler); SPL_STEP_WPC=4 selects the 4-warp shape
+#define SPL_LAUNCH_STEP(OUT)                                                                 \
+	{                                                                                        \
+		if (L.wpc == 1) {                                                                    \
+			if (do_step) spl_step_kernel<true, 1, OUT><<<L.grid, 32, 0, st>>>(p);             \
+			else spl_step_kernel<false, 1, OUT><<<L.grid, 32, 0, st>>>(p);                    \
+		} else {                                                                             \
+			if (do_step) spl_step_kernel<true, 4, OUT><<<L.grid, 128, 0, st>>>(p);            \
+			else spl_step_kernel<false, 4, OUT><<<L.grid, 128, 0, st>>>(p);                   \
+		}                                                                                    \
+	}
+
 static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, int32_t* obs, int8_t* mask, cudaStream_t st,
                        void* obs_f16 = nullptr, uint8_t* obs_u8 = nullptr) {
 	StepParams p;
@@ -1178,11 +1201,8 @@ static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
-	if (f16) {
-		if (do_step) spl_step_kernel<true, 4, SPL_OUT_F16><<<L.grid, 128, 0, st>>>(p);
-		else spl_step_kernel<false, 4, SPL_OUT_F16><<<L.grid, 128, 0, st>>>(p);
-	} else if (do_step) spl_step_kernel<true, 4, SPL_OUT_I32><<<L.grid, 128, 0, st>>>(p);
-	else spl_step_kernel<false, 4, SPL_OUT_I32><<<L.grid, 128, 0, st>>>(p);
+	if (f16) SPL_LAUNCH_STEP(SPL_OUT_F16)
+	else SPL_LAUNCH_STEP(SPL_OUT_I32)
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
 	g_launches++;
 	return (int)cudaGetLastError();
@@ -1202,8 +1222,7 @@ int spl_launch_compact(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
-	if (do_step) spl_step_kernel<true, 4, SPL_OUT_COMPACT><<<L.grid, 128, 0, st>>>(p);
-	else spl_step_kernel<false, 4, SPL_OUT_COMPACT><<<L.grid, 128, 0, st>>>(p);
+	SPL_LAUNCH_STEP(SPL_OUT_COMPACT)
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
 	g_launches++;
 	return (int)cudaGetLastError();
