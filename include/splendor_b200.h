@@ -196,6 +196,10 @@ int spl_scripted_action(const int32_t *obs, const int8_t *mask, int64_t n, int k
  * mode 1 = argmax (scripts/eval_suite.py:131-141 model_greedy_policy_from).  logprob / entropy nullable. */
 int spl_masked_sample(const float *logits, const int8_t *mask, int64_t n, int mode, uint64_t env_offset, uint64_t key,
                       uint64_t t, int32_t *actions, float *logprob, float *entropy, void *stream);
+/* the same over fp16 logits with a row pitch (in elements) >= 45, e.g. the output of a half-precision head padded to 48
+ * columns: no float copy of the logits is needed; the arithmetic is done in float on the exactly converted values */
+int spl_masked_sample_f16(const void *logits, int64_t pitch, const int8_t *mask, int64_t n, int mode, uint64_t env_offset,
+                          uint64_t key, uint64_t t, int32_t *actions, float *logprob, float *entropy, void *stream);
 
 /* generalised advantage estimation over step-major [T][n] buffers (ppo_splendor.py:299-314) */
 int spl_gae(const float *rewards, const float *values, const uint8_t *terminals, const float *last_values, int32_t T,

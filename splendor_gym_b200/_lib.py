@@ -37,7 +37,7 @@ EXPORTS = (
     "spl_init", "spl_reset", "spl_step", "spl_observe", "spl_random_action", "spl_export_state", "spl_import_state",
     "spl_dual_combine", "spl_error_string", "spl_version", "spl_host_ret_table", "spl_launch_count",
     "spl_timing_enable", "spl_timing_read", "spl_rollout_random", "spl_scripted_action", "spl_masked_sample", "spl_gae",
-    "spl_host_create", "spl_host_destroy", "spl_host_step", "spl_host_observe", "spl_host_set_threads", "spl_host_expand", "spl_rollout_plan", "spl_observe_policy",
+    "spl_host_create", "spl_host_destroy", "spl_host_step", "spl_host_observe", "spl_host_set_threads", "spl_host_expand", "spl_rollout_plan", "spl_observe_policy", "spl_masked_sample_f16",
 )
 
 BOT_RANDOM, BOT_GREEDY_V1, BOT_BASIC_PRIORITY, BOT_GREEDY_V2 = 0, 1, 2, 3
@@ -107,6 +107,8 @@ def load():
     L.spl_scripted_action.argtypes = [vp, vp, i64, C.c_int, u64, u64, u64, vp, vp]
     L.spl_masked_sample.restype = C.c_int
     L.spl_masked_sample.argtypes = [vp, vp, i64, C.c_int, u64, u64, u64, vp, vp, vp, vp]
+    L.spl_masked_sample_f16.restype = C.c_int
+    L.spl_masked_sample_f16.argtypes = [vp, i64, vp, i64, C.c_int, u64, u64, u64, vp, vp, vp, vp]
     L.spl_gae.restype = C.c_int
     L.spl_gae.argtypes = [vp, vp, vp, vp, C.c_int32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.spl_observe.restype = C.c_int

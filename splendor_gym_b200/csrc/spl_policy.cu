@@ -5,6 +5,7 @@
 //     scripts/eval_suite.py:131-141)                                                  -> spl_masked_sample
 //   * generalised advantage estimation of ppo_splendor.py:299-314                     -> spl_gae
 // These are small elementwise kernels; they are not on the roofline-critical path.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -132,9 +133,11 @@ __global__ void __launch_bounds__(128) spl_scripted_action_kernel(const int32_t*
 // mode 1: argmax (first maximum, like torch.argmax).  Rows without any legal action are left unmasked
 // (ppo_splendor.py:27-38).  logprob (nullable) = log softmax of the masked logits at the chosen action,
 // entropy (nullable) per env.
-__global__ void __launch_bounds__(128) spl_masked_sample_kernel(const float* __restrict__ logits, const int8_t* __restrict__ mask, int64_t n, int mode,
-                                                              uint64_t env_offset, uint64_t key, uint64_t t, int32_t* __restrict__ actions,
-                                                              float* __restrict__ logprob, float* __restrict__ entropy) {
+template <typename LT>
+__global__ void __launch_bounds__(128) spl_masked_sample_kernel(const LT* __restrict__ logits, int64_t pitch, const int8_t* __restrict__ mask,
+                                                              int64_t n, int mode, uint64_t env_offset, uint64_t key, uint64_t t,
+                                                              int32_t* __restrict__ actions, float* __restrict__ logprob,
+                                                              float* __restrict__ entropy) {
 	__shared__ uint8_t rows_s[4][32 * SPL_NUM_ACTIONS];
 	__shared__ float lg_s[4][32 * SPL_NUM_ACTIONS + 1];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -142,8 +145,15 @@ __global__ void __launch_bounds__(128) spl_masked_sample_kernel(const float* __r
 	for (int64_t ti = (int64_t)blockIdx.x * 4 + warp; ti < ntiles; ti += (int64_t)gridDim.x * 4) {
 		const int rows = (int)min((int64_t)32, n - ti * 32);
 		uint64_t m = pol_load_mask(mask, ti, rows, rows_s[warp], lane);
-		const float* g = logits + ti * 32 * SPL_NUM_ACTIONS;
-		for (int b = lane; b < rows * SPL_NUM_ACTIONS; b += 32) lg_s[warp][b] = g[b];  // coalesced tile load
+		const LT* g = logits + ti * 32 * pitch;
+		if (pitch == SPL_NUM_ACTIONS) {
+			for (int b = lane; b < rows * SPL_NUM_ACTIONS; b += 32) lg_s[warp][b] = (float)g[b];  // coalesced tile load
+		} else {  // padded rows (e.g. an output layer rounded up to 48 columns): skip the padding
+			for (int b = lane; b < rows * SPL_NUM_ACTIONS; b += 32) {
+				const int r = b / SPL_NUM_ACTIONS, a = b - r * SPL_NUM_ACTIONS;
+				lg_s[warp][b] = (float)g[r * pitch + a];
+			}
+		}
 		__syncwarp();
 		if (lane < rows) {
 			const int64_t env = ti * 32 + lane;
@@ -224,8 +234,18 @@ int spl_masked_sample(const float* logits, const int8_t* mask, int64_t n, int mo
                       int32_t* actions, float* logprob, float* entropy, void* stream) {
 	if (!logits || !mask || !actions || n <= 0 || (mode != 0 && mode != 1)) return SPL_E_BADARG;
 	int64_t ctas = ((n + 31) / 32 + 3) / 4;
-	spl_masked_sample_kernel<<<(int)(ctas < 148 * 8 ? ctas : 148 * 8), 128, 0, (cudaStream_t)stream>>>(logits, mask, n, mode, env_offset, key, t,
-	                                                                                                actions, logprob, entropy);
+	spl_masked_sample_kernel<float><<<(int)(ctas < 148 * 8 ? ctas : 148 * 8), 128, 0, (cudaStream_t)stream>>>(
+	    logits, SPL_NUM_ACTIONS, mask, n, mode, env_offset, key, t, actions, logprob, entropy);
+	g_launches++;
+	return (int)cudaGetLastError();
+}
+
+int spl_masked_sample_f16(const void* logits, int64_t pitch, const int8_t* mask, int64_t n, int mode, uint64_t env_offset, uint64_t key,
+                          uint64_t t, int32_t* actions, float* logprob, float* entropy, void* stream) {
+	if (!logits || !mask || !actions || n <= 0 || pitch < SPL_NUM_ACTIONS || (mode != 0 && mode != 1)) return SPL_E_BADARG;
+	int64_t ctas = ((n + 31) / 32 + 3) / 4;
+	spl_masked_sample_kernel<__half><<<(int)(ctas < 148 * 8 ? ctas : 148 * 8), 128, 0, (cudaStream_t)stream>>>(
+	    (const __half*)logits, pitch, mask, n, mode, env_offset, key, t, actions, logprob, entropy);
 	g_launches++;
 	return (int)cudaGetLastError();
 }

@@ -42,17 +42,22 @@ def bot_policy(kind: str, key: int = 0xB07):
 
 def masked_sample(logits: torch.Tensor, mask: torch.Tensor, *, greedy: bool = False, key: int = 0x5A11, t: int = 0, env_offset: int = 0,
                   want_logprob: bool = True, want_entropy: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """Masked categorical over ``logits [N,45]`` (float32): sample (ppo_splendor.py:27-38,54-59) or argmax
+    """Masked categorical over ``logits [N,45]`` (float32, or float16 with any row pitch): sample (ppo_splendor.py:27-38,54-59) or argmax
     (scripts/eval_suite.py:131-141).  Returns (actions int32, log_prob, entropy)."""
     n = mask.shape[0]
-    logits = logits.float().contiguous()
     actions = torch.empty(n, dtype=torch.int32, device=mask.device)
     logprob = torch.empty(n, dtype=torch.float32, device=mask.device) if want_logprob else None
     entropy = torch.empty(n, dtype=torch.float32, device=mask.device) if want_entropy else None
+    lp, en = (None if logprob is None else logprob.data_ptr()), (None if entropy is None else entropy.data_ptr())
     with torch.cuda.device(mask.device):
-        L.check(L.load().spl_masked_sample(logits.data_ptr(), mask.data_ptr(), n, 1 if greedy else 0, env_offset, key, t, actions.data_ptr(),
-                                           None if logprob is None else logprob.data_ptr(), None if entropy is None else entropy.data_ptr(),
-                                           _stream(mask)), "spl_masked_sample")
+        if logits.dtype == torch.float16 and logits.dim() == 2 and logits.stride(1) == 1 and logits.shape[1] >= L.NUM_ACTIONS:
+            # half-precision head, possibly a column slice of a padded output ([:, :45] of [N, 48]): read in place
+            L.check(L.load().spl_masked_sample_f16(logits.data_ptr(), logits.stride(0), mask.data_ptr(), n, 1 if greedy else 0, env_offset,
+                                                   key, t, actions.data_ptr(), lp, en, _stream(mask)), "spl_masked_sample_f16")
+        else:
+            logits = logits.float().contiguous()
+            L.check(L.load().spl_masked_sample(logits.data_ptr(), mask.data_ptr(), n, 1 if greedy else 0, env_offset, key, t,
+                                               actions.data_ptr(), lp, en, _stream(mask)), "spl_masked_sample")
     return actions, logprob, entropy
 
 

@@ -52,6 +52,28 @@ def test_bots_drive_dual_step():
     assert st[0] > 2000 and st[1] + st[2] + st[3] + st[4] + st[5] == st[0]
 
 
+def test_masked_sample_f16_pitched_equals_float_path():
+    """fp16 logits read in place from a padded [N,48] head (spl_masked_sample_f16) give exactly the results of the float path
+    on the same values: actions, log-probs, entropy."""
+    from splendor_gym_b200.policy import masked_sample
+
+    torch.manual_seed(2)
+    n = 5000
+    head = (torch.randn(n, 48, device="cuda") * 2).half()
+    mask = (torch.rand(n, 45, device="cuda") < 0.3).to(torch.int8)
+    mask[:5] = 0
+    view = head[:, :45]
+    assert not view.is_contiguous()
+    for greedy in (False, True):
+        a1, lp1, e1 = masked_sample(view, mask, greedy=greedy, t=4, want_entropy=True)
+        a2, lp2, e2 = masked_sample(view.float().contiguous(), mask, greedy=greedy, t=4, want_entropy=True)
+        assert torch.equal(a1, a2) and torch.equal(lp1, lp2) and torch.equal(e1, e2)
+    dense = head[:, :45].contiguous()  # pitch 45, unaligned rows
+    a3, lp3, _ = masked_sample(dense, mask, t=4)
+    a4, lp4, _ = masked_sample(dense.float(), mask, t=4)
+    assert torch.equal(a3, a4) and torch.equal(lp3, lp4)
+
+
 def test_masked_sample_against_torch():
     from splendor_gym_b200.policy import masked_sample
 
