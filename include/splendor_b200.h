@@ -105,6 +105,10 @@ typedef struct spl_envs {
 	uint64_t seed_base;  /* engine seed of (global env g, episode e) = (seed_base + 1000003 e + g) mod (2^31-1) */
 	int32_t shuffle_mode; /* SPL_SHUFFLE_* */
 	int32_t reserved_;
+	uint8_t *spare;      /* nullable, SPL_SHUFFLE_MT19937 only: [n][SPL_DECK_STRIDE] prefetched deal of every env's NEXT episode
+	                        followed by int32[n + 4] (refill list), i.e. n * 96 + (n + 4) * 4 bytes, 16-byte aligned.  With it the
+	                        bit-exact auto-reset no longer waits for one lane's random.Random(seed) chain (~35 us) every
+	                        lock-step: spl_step takes the prepared deal and refills the spares in batches.  Zero it once. */
 } spl_envs_t;
 
 /* Outputs of one lock-step (the 5-tuple of SplendorEnv.step, batched). Nullable members are skipped. */

@@ -49,7 +49,7 @@ class SplEnvs(C.Structure):
     _fields_ = [
         ("state", C.c_void_p), ("decks", C.c_void_p), ("episode", C.c_void_p), ("scratch", C.c_void_p),
         ("stride", C.c_int64), ("n", C.c_int64), ("env_offset", C.c_uint64), ("seed_base", C.c_uint64),
-        ("shuffle_mode", C.c_int32), ("reserved_", C.c_int32),
+        ("shuffle_mode", C.c_int32), ("reserved_", C.c_int32), ("spare", C.c_void_p),
     ]
 
 

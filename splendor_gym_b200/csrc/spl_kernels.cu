@@ -284,6 +284,7 @@ __device__ __forceinline__ void spl_state_from_deal(SplState& s, const uint32_t 
 #define SPL_RESET_NONE 0
 #define SPL_RESET_WORKLIST 1 /* queue finished envs for spl_reset_kernel (MT19937 shuffles need 2.5 KB of state per env) */
 #define SPL_RESET_FUSED 2    /* deal the new episode right here (Philox) */
+#define SPL_RESET_SPARE 3    /* MT19937 with a prefetched deal of the NEXT episode per env (spl_envs_t.spare): take it right here */
 
 struct StepParams {
 	uint4* state;
@@ -305,6 +306,7 @@ struct StepParams {
 	uint64_t action_key, action_t;
 	const uint64_t* action_t_base;
 	int reset_mode;
+	uint8_t* spare;      // SPL_RESET_SPARE: [n][96] prefetched deals, then the int32 refill list (header of 4 + n entries)
 	int vec_ok;  // obs / mask bases are 16-byte aligned (and, for step-major buffers, every step's slice is)
 	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
 	int sync;    // rollout kernel: CTA barrier per lock-step (keeps the warps of a CTA in the same code region)
@@ -354,11 +356,54 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 	}
 	uint32_t rb = __ballot_sync(SPL_FULL, do_reset);
 	if (rb == 0) return;
-	if (p.reset_mode == SPL_RESET_WORKLIST) {
+	if (p.reset_mode == SPL_RESET_SPARE) {
+		// The deal of every env's NEXT episode was computed ahead of time, off the critical path (one lane's
+		// random.Random(seed) chain takes ~35 us): copy it in, mark it consumed and queue the env for a refill.
+		// A spare that is not there (two finishes of one env between refills: cannot happen in legal play with the
+		// refill age used, but hand-built states may) falls back to the work list below.
+		int32_t* const refill = reinterpret_cast<int32_t*>(p.spare + p.n * SPL_DECK_STRIDE);
+		uint32_t late = 0;
+		for (uint32_t todo = rb; todo;) {
+			const int src = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const int64_t e = __shfl_sync(SPL_FULL, env, src);
+			uint32_t* srow = reinterpret_cast<uint32_t*>(p.spare + e * SPL_DECK_STRIDE);
+			const uint32_t wv = lane < 24 ? __ldcg(srow + lane) : 0u;
+			if ((__shfl_sync(SPL_FULL, wv, 23) >> 24) == 0u) {  // byte 95: ready flag
+				late |= 1u << src;
+				continue;
+			}
+			if (lane < 24)  // deck row: bytes 90.. are padding there
+				reinterpret_cast<uint32_t*>(p.decks + e * SPL_DECK_STRIDE)[lane] = lane == 22 ? (wv | 0xFFFF0000u) : (lane == 23 ? 0xFFFFFFFFu : wv);
+			const uint32_t w8 = __shfl_sync(SPL_FULL, wv, 8), w9 = __shfl_sync(SPL_FULL, wv, 9), w16 = __shfl_sync(SPL_FULL, wv, 16);
+			const uint32_t w17 = __shfl_sync(SPL_FULL, wv, 17), w21 = __shfl_sync(SPL_FULL, wv, 21), w22 = __shfl_sync(SPL_FULL, wv, 22);
+			const uint32_t w23 = __shfl_sync(SPL_FULL, wv, 23);
+			if (lane == 23) srow[23] = 0u;  // consumed
+			if (lane == 0) {
+				const int idx = atomicAdd(refill, 1);
+				refill[4 + idx] = (int32_t)e;
+				const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
+				atomicCAS(reinterpret_cast<unsigned int*>(refill + 1), 0u, (unsigned int)now + 1u);  // age of the oldest entry
+			}
+			if (lane == src) {
+				p.episode[env] = __ldcg(p.episode + env) + 1u;
+				uint32_t board[3];
+				board[0] = __byte_perm(w9, 0, 0x0123);     // deck1[39],[38],[37],[36] (engine/state.py:190-191: pop() from the end)
+				board[1] = __byte_perm(w16, w17, 0x2345);  // deck2 = bytes 40..69
+				board[2] = __byte_perm(w21, w22, 0x2345);  // deck3 = bytes 70..89
+				spl_state_from_deal(s, board, (w22 >> 16) | ((w23 & 0xFFu) << 16));  // bytes 90..92: the three visible nobles
+				if (tops != nullptr) *tops = (w8 >> 24) | (((w16 >> 8) & 0xFFu) << 8) | (((w21 >> 8) & 0xFFu) << 16);  // bytes 35, 65, 85
+			}
+		}
+		rb = late;
+		if (rb == 0) return;
+	}
+	if (p.reset_mode == SPL_RESET_WORKLIST || p.reset_mode == SPL_RESET_SPARE) {
+		const bool mine = (rb >> lane) & 1u;
 		int base = 0;
 		if (lane == 0) base = atomicAdd(p.scratch, __popc(rb));
 		base = __shfl_sync(SPL_FULL, base, 0);
-		if (do_reset) p.scratch[4 + base + __popc(rb & ((1u << lane) - 1u))] = (int32_t)env;
+		if (mine) p.scratch[4 + base + __popc(rb & ((1u << lane) - 1u))] = (int32_t)env;
 	} else {
 		while (rb) {  // warp-uniform loop over the lanes whose episode just ended
 			const int src = __ffs(rb) - 1;
@@ -652,6 +697,9 @@ struct ResetParams {
 	int32_t* next_action;  // nullable: fused random-legal sampler for the fresh state
 	uint64_t action_key, action_t;
 	const uint64_t* action_t_base;
+	uint8_t* spare_out;  // non-null: do NOT reset anything; deal episode[env] + 1 of every listed env into its spare row
+	int32_t* refill;     // with spare_out: the list is the refill list; run only when it is old / long enough, then clear it
+	int refill_age, refill_count;
 };
 
 // MT19937 state of one lane, lane-interleaved in shared memory (conflict-free).  The generator sits on the critical
@@ -769,8 +817,15 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	uint8_t* decks_s = smem + sizeof(SplTables) + SPL_TILE_WORDS * 4;
 	uint32_t* mt_s = reinterpret_cast<uint32_t*>(decks_s + 32 * SPL_DECK_SMEM);
 	const int lane = threadIdx.x;
-	spl_stage_tables<32>(T);
 	const int64_t count = p.list ? (int64_t)p.list[0] : p.n;
+	if (p.refill != nullptr) {  // refill launch (every lock-step): almost always nothing to do yet
+		const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
+		const uint32_t oldest = (uint32_t)p.refill[1];
+		const bool due = count > 0 && (count >= p.refill_count || (oldest != 0u && (uint32_t)now + 1u - oldest >= (uint32_t)p.refill_age));
+		if (!due) return;
+	}
+	if (count == 0) return;
+	spl_stage_tables<32>(T);
 	// A work list (auto-reset of the envs that just finished) is short and sits on the critical path of the lock-step:
 	// spread it over every warp of the grid -- `ipw` items per warp instead of 32 -- so that the serial parts (one
 	// lane's MT19937 chain, one scattered output row per iteration) run side by side on all SMs.
@@ -788,11 +843,16 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 		uint32_t w[16];
 		uint32_t ep = 0;
 		uint64_t seed = 0;
+		const bool spare_mode = SHUFFLE == SPL_SHUFFLE_MT19937 && p.spare_out != nullptr;
 		if (valid) {
-			ep = p.bump_episode ? p.episode[env] + 1u : 0u;
-			p.episode[env] = ep;
+			if (spare_mode) {
+				ep = p.episode[env] + 1u;  // the episode AFTER the current one; the counter itself moves when the spare is taken
+			} else {
+				ep = p.bump_episode ? p.episode[env] + 1u : 0u;
+				p.episode[env] = ep;
+			}
 			uint64_t genv = p.env_offset + (uint64_t)env;
-			seed = p.seeds ? p.seeds[env] : (p.seed_base + 1000003ull * ep + genv) % 2147483647ull;
+			seed = (p.seeds && !spare_mode) ? p.seeds[env] : (p.seed_base + 1000003ull * ep + genv) % 2147483647ull;
 		}
 		spl_fresh_state(s);
 		if (SHUFFLE == SPL_SHUFFLE_MT19937) {
@@ -801,11 +861,16 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 				rng.mt = mt_s + lane;
 				rng.seed(seed);
 				spl_deal(rng, deck, s);
+				if (spare_mode) {  // bytes 90..92: visible nobles, 95: ready
+					deck[90] = (uint8_t)(s.nobles & 0xFFu), deck[91] = (uint8_t)((s.nobles >> 8) & 0xFFu), deck[92] = (uint8_t)((s.nobles >> 16) & 0xFFu);
+					deck[93] = 0, deck[94] = 0, deck[95] = 1;
+				}
 				const uint32_t* d4 = reinterpret_cast<const uint32_t*>(deck);
-				uint32_t* g4 = reinterpret_cast<uint32_t*>(p.decks + env * SPL_DECK_STRIDE);
+				uint32_t* g4 = reinterpret_cast<uint32_t*>((spare_mode ? p.spare_out : p.decks) + env * SPL_DECK_STRIDE);
 #pragma unroll
 				for (int k = 0; k < SPL_DECK_STRIDE / 4; k++) g4[k] = d4[k];
 			}
+			if (spare_mode) continue;  // nothing else changes
 		} else {
 			// same warp-cooperative deal as the fused auto-reset of the step kernel, one environment at a time
 			const uint32_t vb = __ballot_sync(SPL_FULL, valid);
@@ -855,6 +920,15 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 				}
 			}
 			__syncwarp();
+		}
+	}
+	if (p.refill != nullptr) {  // every CTA read the header before it got here: the last one to arrive empties the list
+		__syncwarp();
+		if (lane == 0) {
+			__threadfence();
+			if (atomicAdd(reinterpret_cast<unsigned int*>(p.refill + 2), 1u) == gridDim.x - 1u) {
+				p.refill[0] = 0, p.refill[1] = 0, p.refill[2] = 0;
+			}
 		}
 	}
 }
@@ -1074,13 +1148,27 @@ int spl_init(void) {
 
 static int check_envs(const spl_envs_t* e) {
 	if (!e || !e->state || !e->decks || !e->episode || !e->scratch || e->n <= 0 || e->stride < e->n) return SPL_E_BADARG;
-	if (((uintptr_t)e->state & 15) || ((uintptr_t)e->decks & 15)) return SPL_E_ALIGN;
+	if (((uintptr_t)e->state & 15) || ((uintptr_t)e->decks & 15) || ((uintptr_t)e->spare & 15)) return SPL_E_ALIGN;
 	if (g_inited_device < 0) return SPL_E_NOTINIT;
 	return 0;
 }
 
+static int env_int(const char* name, int dflt) {
+	const char* e = getenv(name);
+	return e ? atoi(e) : dflt;
+}
+
+// SPARE_FILL: deal the NEXT episode of the listed envs into their spare rows; SPARE_REFILL: the same for the refill
+// list kept behind the spare rows, run only when the list is old / long enough (decided on the device)
+#define SPL_RESET_NORMAL 0
+#define SPL_RESET_SPARE_FILL 1
+#define SPL_RESET_SPARE_REFILL 2
+#define SPL_SPARE_REFILL_AGE 12 /* lock-steps; a game lasts >= 17 moves, so a spare is back before its env can need it */
+
+static int32_t* spare_list(const spl_envs_t* e) { return reinterpret_cast<int32_t*>(e->spare + e->n * SPL_DECK_STRIDE); }
+
 static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t* seeds, int bump, int32_t* obs, int8_t* mask,
-                        cudaStream_t st, const spl_step_io_t* io = nullptr) {
+                        cudaStream_t st, const spl_step_io_t* io = nullptr, int kind = SPL_RESET_NORMAL) {
 	ResetParams p;
 	p.next_action = io ? io->next_action : nullptr;
 	p.action_key = io ? io->action_key : 0, p.action_t = io ? io->action_t : 0;
@@ -1088,6 +1176,16 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 	p.state = (uint4*)e->state, p.stride = e->stride, p.decks = e->decks, p.episode = e->episode, p.list = list;
 	p.n = e->n, p.env_offset = e->env_offset, p.seed_base = e->seed_base, p.seeds = seeds, p.obs = obs, p.mask = mask;
 	p.bump_episode = bump;
+	p.spare_out = nullptr, p.refill = nullptr, p.refill_age = 0, p.refill_count = 0;
+	if (kind != SPL_RESET_NORMAL) {
+		if (e->shuffle_mode != SPL_SHUFFLE_MT19937 || e->spare == nullptr) return SPL_E_BADARG;
+		p.spare_out = e->spare, p.obs = nullptr, p.mask = nullptr, p.next_action = nullptr, p.seeds = nullptr;
+		if (kind == SPL_RESET_SPARE_REFILL) {
+			p.list = spare_list(e), p.refill = spare_list(e);
+			p.refill_age = env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE);
+			p.refill_count = (int)(e->n / 2 > 0 ? e->n / 2 : 1);
+		}
+	}
 	int64_t groups = (e->n + 31) / 32;
 	if (e->shuffle_mode == SPL_SHUFFLE_MT19937) {
 		int grid = (int)(groups < (int64_t)g_num_sms * 2 ? groups : (int64_t)g_num_sms * 2);
@@ -1106,12 +1204,20 @@ int spl_reset(const spl_envs_t* envs, const uint64_t* seeds, const uint8_t* rese
 	int rc = check_envs(envs);
 	if (rc) return rc;
 	cudaStream_t st = (cudaStream_t)stream;
-	if (reset_mask == nullptr) return launch_reset(envs, nullptr, seeds, 0, obs, mask, st);
+	const bool spares = envs->spare != nullptr && envs->shuffle_mode == SPL_SHUFFLE_MT19937;
+	if (reset_mask == nullptr) {
+		rc = launch_reset(envs, nullptr, seeds, 0, obs, mask, st);
+		if (rc || !spares) return rc;
+		SPL_CUDA(cudaMemsetAsync(spare_list(envs), 0, 16, st));  // nothing waits for a refill any more
+		return launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, nullptr, SPL_RESET_SPARE_FILL);
+	}
 	SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, 16, st));
 	spl_compact_kernel<<<(unsigned)((envs->n + 255) / 256), 256, 0, st>>>(reset_mask, envs->n, envs->scratch);
 	g_launches++;
 	SPL_CUDA(cudaGetLastError());
-	return launch_reset(envs, envs->scratch, seeds, 1, obs, mask, st);
+	rc = launch_reset(envs, envs->scratch, seeds, 1, obs, mask, st);
+	if (rc || !spares) return rc;
+	return launch_reset(envs, envs->scratch, nullptr, 0, nullptr, nullptr, st, nullptr, SPL_RESET_SPARE_FILL);
 }
 
 static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_io_t* io, int32_t* obs, int8_t* mask) {
@@ -1125,7 +1231,9 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.action_key = io ? io->action_key : 0, p.action_t = io ? io->action_t : 0;
 	p.action_t_base = io ? io->action_t_base : nullptr;
 	p.reset_mode = SPL_RESET_NONE;
-	if (io && io->autoreset) p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED : SPL_RESET_WORKLIST;
+	p.spare = e->spare;
+	if (io && io->autoreset)
+		p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED : (e->spare ? SPL_RESET_SPARE : SPL_RESET_WORKLIST);
 	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;  // 128-bit tile stores
 	p.steps = 1;
 	p.sync = 0;
@@ -1143,11 +1251,6 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 struct LaunchShape {
 	int wpc, grid, sync, chunk;
 };
-
-static int env_int(const char* name, int dflt) {
-	const char* e = getenv(name);
-	return e ? atoi(e) : dflt;
-}
 
 static LaunchShape launch_shape(int64_t n, int kernel) {
 	const int64_t ntiles = (n + 31) / 32;
@@ -1246,6 +1349,12 @@ int spl_step(const spl_envs_t* envs, const spl_step_io_t* io, void* stream) {
 		// the reset kernel also re-samples next_action for the envs whose mask it replaces
 		rc = launch_reset(envs, envs->scratch, nullptr, 1, io->obs, io->mask, st, io);
 		if (rc) return rc;
+		// prefetched deals: the step kernel took the spares of the envs that finished (the work list above then only
+		// holds the ones that had none); refill them in batches, every SPL_SPARE_REFILL_AGE lock-steps, off the critical path
+		if (envs->spare != nullptr) {
+			rc = launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL);
+			if (rc) return rc;
+		}
 	}
 	return 0;
 }

@@ -66,6 +66,8 @@ class SplendorVecEnv:
     env_offset : global index of env 0 (multi-GPU sharding; results do not depend on the GPU count).
     autoreset : same-step auto-reset as in ppo_splendor.py:245-250 (reward/terminated of the finished
         episode, observation/mask of the new one).
+    prefetch_deals : with ``shuffle="mt19937"`` and auto-reset, keep the deal of every env's next episode ready
+        (``spl_envs_t.spare``) so that a reset does not wait for ``random.Random(seed)`` on the critical path.
     obs_format : ``"int32"`` = the reference's observation dtype (envs/splendor_env.py:34-36).  ``"f16"`` = policy-ready:
         ``self.obs_f16`` is an fp16 ``[N, 304]`` tensor (entries 0..296 = the observation, exact; 297..303 = 0) that an MLP
         consumes without the cast of ppo_splendor.py:221 and with a 16-byte-aligned K, and ``self.obs`` holds the same
@@ -76,7 +78,7 @@ class SplendorVecEnv:
     obs_dim = L.OBS_DIM
 
     def __init__(self, num_envs: int, device="cuda", seed: int = 0, shuffle: str = "philox", env_offset: int = 0,
-                 autoreset: bool = True, obs_format: str = "int32"):
+                 autoreset: bool = True, obs_format: str = "int32", prefetch_deals: bool = True):
         if num_envs <= 0:
             raise ValueError("num_envs must be positive")
         self.lib = L.load()
@@ -115,10 +117,14 @@ class SplendorVecEnv:
         self.info_bits = torch.zeros(n, dtype=torch.uint8, device=d)
         self.stats = torch.zeros(8, dtype=torch.int64, device=d)
         self.next_action = torch.zeros(n, dtype=torch.int32, device=d)
+        # bit-exact decks with auto-reset: prefetched deal of every env's next episode + refill list (struct spl_envs.spare)
+        self.spare = None
+        if self.shuffle_mode == L.SHUFFLE_MT19937 and self.autoreset and prefetch_deals:
+            self.spare = torch.zeros(n * L.DECK_STRIDE + (n + 4) * 4, dtype=torch.uint8, device=d)
         self._envs = L.SplEnvs(
             state=self.state.data_ptr(), decks=self.decks.data_ptr(), episode=self.episode.data_ptr(),
             scratch=self.scratch.data_ptr(), stride=n, n=n, env_offset=int(env_offset), seed_base=int(seed),
-            shuffle_mode=self.shuffle_mode, reserved_=0,
+            shuffle_mode=self.shuffle_mode, reserved_=0, spare=None if self.spare is None else self.spare.data_ptr(),
         )
         # gymnasium.vector-style attributes (what gym.vector.SyncVectorEnv exposes, ppo_splendor.py:151-159)
         from .envs._gym_compat import spaces

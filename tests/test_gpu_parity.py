@@ -397,6 +397,61 @@ def test_rollout_schedule_independence(VecEnv, monkeypatch, chunk, wpc, ctas_per
     assert int(ref[7][0]) > 0
 
 
+@pytest.mark.parametrize("age,prefetch", [(None, True), ("100000", True), ("1", True), (None, False)])
+def test_mt19937_prefetched_deals_bit_exact(VecEnv, oracle, monkeypatch, age, prefetch):
+    """shuffle='mt19937' with auto-reset takes the prefetched deal of each env's next episode (spl_envs_t.spare) and refills the
+    spares in batches.  Whatever the refill cadence -- default, never (every later finish then falls back to the in-line
+    reset kernel), every lock-step -- and without spares at all, every output stays bit-identical to the oracle."""
+    if age is not None:
+        monkeypatch.setenv("SPL_SPARE_REFILL_AGE", age)
+    n, steps = 2048, 260
+    env = VecEnv(n, seed=99, shuffle="mt19937", autoreset=True, prefetch_deals=prefetch)
+    assert (env.spare is not None) == prefetch
+    ref = oracle.OracleVec(n, seed_base=99)
+    obs, info = env.reset()
+    robs, rmask = ref.reset()
+    assert np.array_equal(_np(obs), robs) and np.array_equal(_np(info["action_mask"]), rmask)
+    actions = env.sample_random_actions().clone()
+    for t in range(steps):
+        a = actions.clone()
+        out = env.step(a, sample_next=True)
+        ref_out = ref.step(_np(a), autoreset=True)
+        assert_step_equal(env, out, ref_out, t)
+        actions = env.next_action.clone()
+    assert np.array_equal(_np(env.export_state()), ref.export_rows())
+    assert np.array_equal(_np(env.stats), ref.stats()) and int(env.stats[0]) > 2 * n
+
+
+def test_mt19937_prefetched_deals_survive_manual_resets(VecEnv):
+    """Masked manual resets re-deal the chosen envs AND their spares: an env with prefetched deals stays identical to one
+    without (the in-line reset path, which the oracle tests pin) through auto-resets, masked resets and a full reset."""
+    n = 1024 + 32
+    a = VecEnv(n, seed=5, shuffle="mt19937", autoreset=True, prefetch_deals=True)
+    b = VecEnv(n, seed=5, shuffle="mt19937", autoreset=True, prefetch_deals=False)
+    a.reset()
+    b.reset()
+    actions = a.sample_random_actions().clone()
+    for t in range(300):
+        oa, ra, ta, _, _ = a.step(actions, sample_next=True)
+        ob, rb, tb, _, _ = b.step(actions, sample_next=True)
+        assert torch.equal(oa, ob) and torch.equal(a.mask, b.mask) and torch.equal(ra, rb) and torch.equal(ta, tb), f"step {t}"
+        assert torch.equal(a.info_bits, b.info_bits) and torch.equal(a.next_action, b.next_action)
+        actions = a.next_action.clone()
+        if t in (70, 71, 150):
+            m = torch.zeros(n, dtype=torch.bool, device="cuda")
+            m[t % 5::5] = True
+            a.reset(reset_mask=m)
+            b.reset(reset_mask=m)
+            assert torch.equal(a.obs, b.obs) and torch.equal(a.mask, b.mask)
+            actions = a.sample_random_actions().clone()
+        if t == 220:
+            a.reset()
+            b.reset()
+            actions = a.sample_random_actions().clone()
+    assert torch.equal(a.export_state(), b.export_state()) and torch.equal(a.stats, b.stats) and torch.equal(a.episode, b.episode)
+    assert int(a.stats[0]) > 2 * n
+
+
 def test_fused_reset_equals_reset_kernel(VecEnv):
     """The in-step Philox deal and spl_reset(reset_mask=...) produce the same new episode for (seed, env, episode)."""
     n, T = 4096, 120
