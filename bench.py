@@ -407,6 +407,36 @@ def run_b200(args):
         lockstep = {"value": N * T * k2 / (lms * 1e-3), "unit": UNIT, "what": "per-GPU, one spl_step launch per lock-step (CUDA graph of %d launches)" % T,
                     "us_per_lock_step": 1e3 * lms / (k2 * T)}
         del g2
+        # the same with the reference's own decks (shuffle="mt19937": every deal bit-identical to initial_state(seed),
+        # BASELINE configs[1] "bit-exact replay"); the rollout kernel needs the native Philox deal, this path does not
+        env_mt = SplendorVecEnv(N, device=dev, seed=20261018, shuffle="mt19937", env_offset=rank * N, autoreset=True)
+        env_mt.t_base = env.t_base
+        env_mt.reset()
+        env_mt.sample_random_actions(out=act_buf[0])
+
+        def segment_lockstep_mt():
+            for t in range(T):
+                env_mt._t = t
+                env_mt.step(act_buf[t], out_obs=(obs_buf[t] if write_obs else None), out_mask=mask_buf[t], out_reward=rew_buf[t],
+                            out_terminated=term_buf[t], out_next_action=act_buf[t + 1], write_obs=write_obs)
+            act_buf[0].copy_(act_buf[T])
+            env_mt.t_base += T
+
+        g3 = make_graph(segment_lockstep_mt)
+        for _ in range(2):
+            g3.replay()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(k2):
+            g3.replay()
+        b1.record()
+        torch.cuda.synchronize()
+        lms = b0.elapsed_time(b1)
+        lockstep["bit_exact_decks"] = {"value": N * T * k2 / (lms * 1e-3), "unit": UNIT, "us_per_lock_step": 1e3 * lms / (k2 * T),
+                                       "what": "same, shuffle=mt19937: decks bit-identical to the reference's initial_state(seed); "
+                                               "prefetched next-episode deals (spl_envs_t.spare)"}
+        del g3, env_mt
+        env.sample_random_actions(out=act_buf[0])  # back to the Philox env's own action stream
 
     # ---- end-to-end through the public API with HOST buffers: SplendorVecEnv.step_host (C ABI spl_host_step).
     # Every lock-step: actions from host memory -> device, step kernel, results -> host memory as the reference-typed
