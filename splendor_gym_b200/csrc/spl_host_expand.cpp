@@ -86,10 +86,6 @@ int simd_level() {  // 0 scalar, 2 AVX2, 5 AVX-512 (SPL_HOST_SIMD overrides down
 	}();
 	return v;
 }
-bool have_avx2() {
-	static const bool v = __builtin_cpu_supports("avx2");
-	return v;
-}
 #endif
 
 inline void widen(const uint8_t* src, int32_t* dst, size_t n) {
