@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-obs", action="store_true", help="config 4: mask + step only (no observation encode)")
     ap.add_argument("--shuffle", default="philox", choices=["philox", "mt19937"])
+    ap.add_argument("--deal-slots", type=int, default=8, help="shuffle=mt19937, rollout mode: prefetched deals kept per env")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--mode", default="rollout", choices=["rollout", "lockstep"],
                     help="rollout: one persistent kernel per segment; lockstep: one spl_step launch per lock-step")
@@ -252,7 +253,11 @@ def run_b200(args):
     T = max(1, min(T, int(40e9 // per_step_bytes)))
     write_obs = not args.no_obs
 
-    env = SplendorVecEnv(N, device=dev, seed=20261018, shuffle=args.shuffle, env_offset=rank * N, autoreset=True)
+    use_rollout = args.mode == "rollout"
+    # shuffle="mt19937" (every deal bit-identical to the reference's initial_state(seed)): the rollout kernel takes the deals
+    # from a ring of 8 prefetched ones per env (a game lasts >= 17 moves: 8 cover 128 lock-steps), refilled behind the launch
+    env = SplendorVecEnv(N, device=dev, seed=20261018, shuffle=args.shuffle, env_offset=rank * N, autoreset=True,
+                         prefetch_deals=(args.deal_slots if use_rollout else True))
     obs_buf = torch.zeros((T, N, 297), dtype=torch.int32, device=dev) if write_obs else None
     mask_buf = torch.zeros((T, N, 45), dtype=torch.int8, device=dev)
     rew_buf = torch.zeros((T, N), dtype=torch.float32, device=dev)
@@ -278,7 +283,6 @@ def run_b200(args):
         act_buf[0].copy_(act_buf[T])
         env.t_base += T
 
-    use_rollout = args.mode == "rollout" and args.shuffle == "philox"
     segment = segment_rollout if use_rollout else segment_lockstep
     launches0 = lib.spl_launch_count()
     segment()  # eager once (also validates arguments)

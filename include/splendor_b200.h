@@ -32,6 +32,7 @@ extern "C" {
 #define SPL_STATE_PLANES 4 /* packed hot state: 4 planes of 16 B per env = 64 B */
 #define SPL_DECK_STRIDE 96 /* bytes per env of deck order (90 used: tier1[40] tier2[30] tier3[20]) */
 #define SPL_RET_TABLE_LEN 8910
+#define SPL_MAX_SPARE_SLOTS 16
 
 /* info byte written per env by spl_step (envs/splendor_env.py:56-88 info dict, flattened) */
 #define SPL_INFO_ILLEGAL 1u      /* info["illegal_action"]: reward -0.01, state unchanged (:64-66) */
@@ -104,11 +105,14 @@ typedef struct spl_envs {
 	uint64_t env_offset; /* global id of env 0 (multi-GPU sharding: seeds depend on the global id only) */
 	uint64_t seed_base;  /* engine seed of (global env g, episode e) = (seed_base + 1000003 e + g) mod (2^31-1) */
 	int32_t shuffle_mode; /* SPL_SHUFFLE_* */
-	int32_t reserved_;
-	uint8_t *spare;      /* nullable, SPL_SHUFFLE_MT19937 only: [n][SPL_DECK_STRIDE] prefetched deal of every env's NEXT episode
-	                        followed by int32[n + 4] (refill list), i.e. n * 96 + (n + 4) * 4 bytes, 16-byte aligned.  With it the
-	                        bit-exact auto-reset no longer waits for one lane's random.Random(seed) chain (~35 us) every
-	                        lock-step: spl_step takes the prepared deal and refills the spares in batches.  Zero it once. */
+	int32_t spare_slots; /* S = deals kept ahead per env in `spare` (0 or 1 = one; at most SPL_MAX_SPARE_SLOTS) */
+	uint8_t *spare;      /* nullable, SPL_SHUFFLE_MT19937 only: [n][S][SPL_DECK_STRIDE] prefetched deals of every env's NEXT S
+	                        episodes (episode e in slot e % S, tagged with e) followed by int32[n * S + 4] (refill list), i.e.
+	                        n * S * 96 + (n * S + 4) * 4 bytes, 16-byte aligned.  With it the bit-exact auto-reset no longer
+	                        waits for one lane's random.Random(seed) chain (~35 us): spl_step takes the prepared deal and
+	                        refills the spares in batches; spl_rollout_random (one launch for many lock-steps) takes up to S
+	                        per env and refills behind the launch -- a game lasts >= 17 moves, so S = 8 covers 128 lock-steps
+	                        (an env that runs out is dealt in place, slowly).  Zero it once. */
 } spl_envs_t;
 
 /* Outputs of one lock-step (the 5-tuple of SplendorEnv.step, batched). Nullable members are skipped. */
@@ -155,7 +159,7 @@ int spl_step(const spl_envs_t *envs, const spl_step_io_t *io, void *stream);
  * [steps][n][45], reward / terminated / info [steps][n]; io->actions = actions of the first step [n];
  * io->next_action = [steps+1][n] (row 0 is left untouched, row t+1 = action chosen after step t).
  * Results are bit-identical to `steps` chained spl_step calls with action_t, action_t+1, ...
- * Requires SPL_SHUFFLE_PHILOX and autoreset. */
+ * Requires autoreset and either SPL_SHUFFLE_PHILOX or SPL_SHUFFLE_MT19937 with prefetched deals (envs->spare). */
 int spl_rollout_random(const spl_envs_t *envs, const spl_step_io_t *io, int32_t steps, void *stream);
 
 /* How spl_rollout_random would run `steps` lock-steps of n envs on the current device (measurement aid):

@@ -18,6 +18,7 @@ ROW_LEN = 166
 STATE_PLANES = 4
 DECK_STRIDE = 96
 RET_TABLE_LEN = 8910
+MAX_SPARE_SLOTS = 16
 
 INFO_ILLEGAL = 1
 INFO_NOLEGAL_DRAW = 2
@@ -49,7 +50,7 @@ class SplEnvs(C.Structure):
     _fields_ = [
         ("state", C.c_void_p), ("decks", C.c_void_p), ("episode", C.c_void_p), ("scratch", C.c_void_p),
         ("stride", C.c_int64), ("n", C.c_int64), ("env_offset", C.c_uint64), ("seed_base", C.c_uint64),
-        ("shuffle_mode", C.c_int32), ("reserved_", C.c_int32), ("spare", C.c_void_p),
+        ("shuffle_mode", C.c_int32), ("spare_slots", C.c_int32), ("spare", C.c_void_p),
     ]
 
 

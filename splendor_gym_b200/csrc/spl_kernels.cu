@@ -284,7 +284,8 @@ __device__ __forceinline__ void spl_state_from_deal(SplState& s, const uint32_t 
 #define SPL_RESET_NONE 0
 #define SPL_RESET_WORKLIST 1 /* queue finished envs for spl_reset_kernel (MT19937 shuffles need 2.5 KB of state per env) */
 #define SPL_RESET_FUSED 2    /* deal the new episode right here (Philox) */
-#define SPL_RESET_SPARE 3    /* MT19937 with a prefetched deal of the NEXT episode per env (spl_envs_t.spare): take it right here */
+#define SPL_RESET_SPARE 3    /* MT19937 with prefetched deals of the NEXT episode(s) per env (spl_envs_t.spare): take it right here */
+#define SPL_RESET_SPARE_INLINE 4 /* the same inside the rollout kernel: a missing spare is dealt in place by one lane (slow, rare) */
 
 struct StepParams {
 	uint4* state;
@@ -306,7 +307,8 @@ struct StepParams {
 	uint64_t action_key, action_t;
 	const uint64_t* action_t_base;
 	int reset_mode;
-	uint8_t* spare;      // SPL_RESET_SPARE: [n][96] prefetched deals, then the int32 refill list (header of 4 + n entries)
+	uint8_t* spare;      // SPL_RESET_SPARE: [n][slots][96] prefetched deals, then the int32 refill list (header of 4 + n*slots entries)
+	int spare_slots;     // deals kept ahead per env (ring indexed by episode % slots)
 	int vec_ok;  // obs / mask bases are 16-byte aligned (and, for step-major buffers, every step's slice is)
 	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
 	int sync;    // rollout kernel: CTA barrier per lock-step (keeps the warps of a CTA in the same code region)
@@ -323,6 +325,11 @@ struct SplTile {
 	int64_t ti;      // tile index; env = ti*32 + lane
 	int rows;        // valid envs in the tile
 };
+
+// initial_state(seed) by ONE lane, MT19937 state in `smem` (>= 656 words), deck row to global memory (defined below);
+// results in smem[648..652]: board rows, visible nobles, deck tops (no reference arguments: nothing of the caller is
+// forced onto the stack)
+__device__ __noinline__ void spl_mt_deal_in_place(uint64_t seed, uint32_t* smem, uint8_t* deck_row);
 
 // one SplendorEnv.step for the lane's env + episode statistics + same-step auto-reset
 template <bool KNOWN_MASK>
@@ -356,20 +363,25 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 	}
 	uint32_t rb = __ballot_sync(SPL_FULL, do_reset);
 	if (rb == 0) return;
-	if (p.reset_mode == SPL_RESET_SPARE) {
-		// The deal of every env's NEXT episode was computed ahead of time, off the critical path (one lane's
-		// random.Random(seed) chain takes ~35 us): copy it in, mark it consumed and queue the env for a refill.
-		// A spare that is not there (two finishes of one env between refills: cannot happen in legal play with the
-		// refill age used, but hand-built states may) falls back to the work list below.
-		int32_t* const refill = reinterpret_cast<int32_t*>(p.spare + p.n * SPL_DECK_STRIDE);
+	if (p.reset_mode == SPL_RESET_SPARE || p.reset_mode == SPL_RESET_SPARE_INLINE) {
+		// The deals of every env's NEXT episodes were computed ahead of time, off the critical path (one lane's
+		// random.Random(seed) chain takes ~35 us): episode e of an env sits in slot e % slots of its ring, tagged with
+		// e.  Copy it in, mark it consumed and queue the slot for a refill.  A spare that is not there (more finishes of
+		// one env between refills than the ring holds: cannot happen in legal play with the refill cadence used, but
+		// hand-built states may) falls back to the work list below / the in-place deal of the rollout kernel.
+		const int64_t R = p.spare_slots;
+		int32_t* const refill = reinterpret_cast<int32_t*>(p.spare + p.n * R * SPL_DECK_STRIDE);
 		uint32_t late = 0;
 		for (uint32_t todo = rb; todo;) {
 			const int src = __ffs(todo) - 1;
 			todo &= todo - 1;
 			const int64_t e = __shfl_sync(SPL_FULL, env, src);
-			uint32_t* srow = reinterpret_cast<uint32_t*>(p.spare + e * SPL_DECK_STRIDE);
+			const uint32_t ep = __ldcg(p.episode + e) + 1u;  // the episode that starts now (L2: another SM may have bumped it)
+			const int64_t code = e * R + (int64_t)(ep % (uint32_t)R);
+			uint32_t* srow = reinterpret_cast<uint32_t*>(p.spare + code * SPL_DECK_STRIDE);
 			const uint32_t wv = lane < 24 ? __ldcg(srow + lane) : 0u;
-			if ((__shfl_sync(SPL_FULL, wv, 23) >> 24) == 0u) {  // byte 95: ready flag
+			const uint32_t w23 = __shfl_sync(SPL_FULL, wv, 23);  // bytes 92..95: third noble, episode tag (16 bits), ready flag
+			if ((w23 >> 24) == 0u || ((w23 >> 8) & 0xFFFFu) != (ep & 0xFFFFu)) {
 				late |= 1u << src;
 				continue;
 			}
@@ -377,16 +389,15 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 				reinterpret_cast<uint32_t*>(p.decks + e * SPL_DECK_STRIDE)[lane] = lane == 22 ? (wv | 0xFFFF0000u) : (lane == 23 ? 0xFFFFFFFFu : wv);
 			const uint32_t w8 = __shfl_sync(SPL_FULL, wv, 8), w9 = __shfl_sync(SPL_FULL, wv, 9), w16 = __shfl_sync(SPL_FULL, wv, 16);
 			const uint32_t w17 = __shfl_sync(SPL_FULL, wv, 17), w21 = __shfl_sync(SPL_FULL, wv, 21), w22 = __shfl_sync(SPL_FULL, wv, 22);
-			const uint32_t w23 = __shfl_sync(SPL_FULL, wv, 23);
 			if (lane == 23) srow[23] = 0u;  // consumed
 			if (lane == 0) {
 				const int idx = atomicAdd(refill, 1);
-				refill[4 + idx] = (int32_t)e;
+				refill[4 + idx] = (int32_t)code;
 				const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
 				atomicCAS(reinterpret_cast<unsigned int*>(refill + 1), 0u, (unsigned int)now + 1u);  // age of the oldest entry
 			}
 			if (lane == src) {
-				p.episode[env] = __ldcg(p.episode + env) + 1u;
+				p.episode[env] = ep;
 				uint32_t board[3];
 				board[0] = __byte_perm(w9, 0, 0x0123);     // deck1[39],[38],[37],[36] (engine/state.py:190-191: pop() from the end)
 				board[1] = __byte_perm(w16, w17, 0x2345);  // deck2 = bytes 40..69
@@ -397,6 +408,23 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 		}
 		rb = late;
 		if (rb == 0) return;
+		if (p.reset_mode == SPL_RESET_SPARE_INLINE) {
+			while (rb) {  // warp-uniform; the serial generator runs on ONE lane with its 624 words in the warp's (idle) tile
+				const int src = __ffs(rb) - 1;
+				rb &= rb - 1;
+				if (lane == src) {
+					const uint32_t ep = __ldcg(p.episode + env) + 1u;
+					p.episode[env] = ep;
+					spl_mt_deal_in_place((p.seed_base + 1000003ull * ep + p.env_offset + (uint64_t)env) % 2147483647ull, tl.smem,
+					                     p.decks + env * SPL_DECK_STRIDE);
+					uint32_t board[3] = {tl.smem[648], tl.smem[649], tl.smem[650]};
+					spl_state_from_deal(s, board, tl.smem[651]);
+					if (tops != nullptr) *tops = tl.smem[652];
+				}
+				__syncwarp();
+			}
+			return;
+		}
 	}
 	if (p.reset_mode == SPL_RESET_WORKLIST || p.reset_mode == SPL_RESET_SPARE) {
 		const bool mine = (rb >> lane) & 1u;
@@ -697,7 +725,9 @@ struct ResetParams {
 	int32_t* next_action;  // nullable: fused random-legal sampler for the fresh state
 	uint64_t action_key, action_t;
 	const uint64_t* action_t_base;
-	uint8_t* spare_out;  // non-null: do NOT reset anything; deal episode[env] + 1 of every listed env into its spare row
+	uint8_t* spare_out;  // non-null: do NOT reset anything; deal upcoming episodes of the listed envs into their spare rows
+	int spare_slots;     // ring slots per env; an item is a code env * slots + slot (refill list / all codes) ...
+	int list_is_envs;    // ... or, for a list of env ids (masked reset), item / slots indexes the list and item % slots is the slot
 	int32_t* refill;     // with spare_out: the list is the refill list; run only when it is old / long enough, then clear it
 	int refill_age, refill_count;
 };
@@ -714,11 +744,12 @@ struct ResetParams {
 #ifndef SPL_MT_LAZY
 #define SPL_MT_LAZY 227 /* a smaller value is still exact (tests build one to exercise the regeneration path) */
 #endif
+template <int STRIDE = 32>
 struct SplMT {
 	uint32_t* mt;
 	int idx;
 	bool twisted;
-	__device__ __forceinline__ uint32_t& at(int i) { return mt[i * 32]; }
+	__device__ __forceinline__ uint32_t& at(int i) { return mt[i * STRIDE]; }
 	__device__ void seed(uint64_t a) {  // random.Random(a): init_by_array over the 32-bit words of a
 		const uint32_t key0 = (uint32_t)a, key1 = (uint32_t)(a >> 32);
 		const bool two = key1 != 0;
@@ -809,6 +840,20 @@ __device__ __forceinline__ void spl_deal(Rng& rng, uint8_t* deck, SplState& s) {
 	s.nobles = (uint32_t)nob[0] | ((uint32_t)nob[1] << 8) | ((uint32_t)nob[2] << 16);
 }
 
+__device__ __noinline__ void spl_mt_deal_in_place(uint64_t seed, uint32_t* smem, uint8_t* deck_row) {
+	SplMT<1> rng;
+	rng.mt = smem;
+	rng.seed(seed);
+	uint8_t* deck = reinterpret_cast<uint8_t*>(smem + 624);
+	SplState s;
+	spl_deal(rng, deck, s);
+	const uint32_t* d4 = reinterpret_cast<const uint32_t*>(deck);
+	uint32_t* g4 = reinterpret_cast<uint32_t*>(deck_row);
+	for (int k = 0; k < SPL_DECK_STRIDE / 4; k++) g4[k] = d4[k];
+	smem[648] = s.board[0], smem[649] = s.board[1], smem[650] = s.board[2], smem[651] = s.nobles;
+	smem[652] = (uint32_t)deck[35] | ((uint32_t)deck[65] << 8) | ((uint32_t)deck[85] << 16);
+}
+
 template <int SHUFFLE>
 __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	extern __shared__ __align__(16) uint8_t smem[];
@@ -817,7 +862,9 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	uint8_t* decks_s = smem + sizeof(SplTables) + SPL_TILE_WORDS * 4;
 	uint32_t* mt_s = reinterpret_cast<uint32_t*>(decks_s + 32 * SPL_DECK_SMEM);
 	const int lane = threadIdx.x;
-	const int64_t count = p.list ? (int64_t)p.list[0] : p.n;
+	const bool spare_mode = SHUFFLE == SPL_SHUFFLE_MT19937 && p.spare_out != nullptr;
+	const int64_t R = spare_mode ? p.spare_slots : 1;
+	const int64_t count = p.list ? (int64_t)p.list[0] * (p.list_is_envs ? R : 1) : p.n * R;
 	if (p.refill != nullptr) {  // refill launch (every lock-step): almost always nothing to do yet
 		const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
 		const uint32_t oldest = (uint32_t)p.refill[1];
@@ -837,16 +884,25 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	for (int64_t g = blockIdx.x; g * ipw < count; g += gridDim.x) {
 		const int64_t item = g * ipw + lane;
 		const bool valid = lane < ipw && item < count;
-		const int64_t env = valid ? (p.list ? (int64_t)p.list[4 + item] : item) : 0;
+		int64_t env = 0, slot = 0;
+		if (valid) {
+			if (!spare_mode) env = p.list ? (int64_t)p.list[4 + item] : item;
+			else if (p.list != nullptr && p.list_is_envs) env = (int64_t)p.list[4 + item / R], slot = item % R;
+			else {
+				const int64_t code = p.list ? (int64_t)p.list[4 + item] : item;
+				env = code / R, slot = code - env * R;
+			}
+		}
 		uint8_t* deck = decks_s + lane * SPL_DECK_SMEM;
 		SplState s;
 		uint32_t w[16];
 		uint32_t ep = 0;
 		uint64_t seed = 0;
-		const bool spare_mode = SHUFFLE == SPL_SHUFFLE_MT19937 && p.spare_out != nullptr;
 		if (valid) {
 			if (spare_mode) {
-				ep = p.episode[env] + 1u;  // the episode AFTER the current one; the counter itself moves when the spare is taken
+				// the first episode AFTER the current one that lives in this slot; the counter itself moves when a spare is taken
+				const uint32_t cur = p.episode[env];
+				ep = cur + 1u + (uint32_t)(((uint32_t)slot + (uint32_t)R - (cur + 1u) % (uint32_t)R) % (uint32_t)R);
 			} else {
 				ep = p.bump_episode ? p.episode[env] + 1u : 0u;
 				p.episode[env] = ep;
@@ -857,16 +913,16 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 		spl_fresh_state(s);
 		if (SHUFFLE == SPL_SHUFFLE_MT19937) {
 			if (valid) {
-				SplMT rng;
+				SplMT<32> rng;
 				rng.mt = mt_s + lane;
 				rng.seed(seed);
 				spl_deal(rng, deck, s);
-				if (spare_mode) {  // bytes 90..92: visible nobles, 95: ready
+				if (spare_mode) {  // bytes 90..92: visible nobles, 93..94: episode tag, 95: ready
 					deck[90] = (uint8_t)(s.nobles & 0xFFu), deck[91] = (uint8_t)((s.nobles >> 8) & 0xFFu), deck[92] = (uint8_t)((s.nobles >> 16) & 0xFFu);
-					deck[93] = 0, deck[94] = 0, deck[95] = 1;
+					deck[93] = (uint8_t)(ep & 0xFFu), deck[94] = (uint8_t)((ep >> 8) & 0xFFu), deck[95] = 1;
 				}
 				const uint32_t* d4 = reinterpret_cast<const uint32_t*>(deck);
-				uint32_t* g4 = reinterpret_cast<uint32_t*>((spare_mode ? p.spare_out : p.decks) + env * SPL_DECK_STRIDE);
+				uint32_t* g4 = reinterpret_cast<uint32_t*>(spare_mode ? p.spare_out + (env * R + slot) * SPL_DECK_STRIDE : p.decks + env * SPL_DECK_STRIDE);
 #pragma unroll
 				for (int k = 0; k < SPL_DECK_STRIDE / 4; k++) g4[k] = d4[k];
 			}
@@ -1163,9 +1219,12 @@ static int env_int(const char* name, int dflt) {
 #define SPL_RESET_NORMAL 0
 #define SPL_RESET_SPARE_FILL 1
 #define SPL_RESET_SPARE_REFILL 2
+#define SPL_RESET_SPARE_REFILL_NOW 3 /* the refill list, unconditionally (after a rollout launch) */
+#define SPL_RESET_SPARE_FILL_ENVS 4  /* every slot of the envs in a list of env ids (masked reset) */
 #define SPL_SPARE_REFILL_AGE 12 /* lock-steps; a game lasts >= 17 moves, so a spare is back before its env can need it */
 
-static int32_t* spare_list(const spl_envs_t* e) { return reinterpret_cast<int32_t*>(e->spare + e->n * SPL_DECK_STRIDE); }
+static int spare_slots(const spl_envs_t* e) { return e->spare_slots > 1 ? (e->spare_slots > SPL_MAX_SPARE_SLOTS ? SPL_MAX_SPARE_SLOTS : e->spare_slots) : 1; }
+static int32_t* spare_list(const spl_envs_t* e) { return reinterpret_cast<int32_t*>(e->spare + e->n * spare_slots(e) * SPL_DECK_STRIDE); }
 
 static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t* seeds, int bump, int32_t* obs, int8_t* mask,
                         cudaStream_t st, const spl_step_io_t* io = nullptr, int kind = SPL_RESET_NORMAL) {
@@ -1177,16 +1236,20 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 	p.n = e->n, p.env_offset = e->env_offset, p.seed_base = e->seed_base, p.seeds = seeds, p.obs = obs, p.mask = mask;
 	p.bump_episode = bump;
 	p.spare_out = nullptr, p.refill = nullptr, p.refill_age = 0, p.refill_count = 0;
+	p.spare_slots = 1, p.list_is_envs = 0;
+	int64_t groups = (e->n + 31) / 32;
 	if (kind != SPL_RESET_NORMAL) {
 		if (e->shuffle_mode != SPL_SHUFFLE_MT19937 || e->spare == nullptr) return SPL_E_BADARG;
 		p.spare_out = e->spare, p.obs = nullptr, p.mask = nullptr, p.next_action = nullptr, p.seeds = nullptr;
-		if (kind == SPL_RESET_SPARE_REFILL) {
+		p.spare_slots = spare_slots(e);
+		p.list_is_envs = kind == SPL_RESET_SPARE_FILL_ENVS;
+		groups *= p.spare_slots;
+		if (kind == SPL_RESET_SPARE_REFILL || kind == SPL_RESET_SPARE_REFILL_NOW) {
 			p.list = spare_list(e), p.refill = spare_list(e);
-			p.refill_age = env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE);
-			p.refill_count = (int)(e->n / 2 > 0 ? e->n / 2 : 1);
+			p.refill_age = kind == SPL_RESET_SPARE_REFILL_NOW ? 0 : env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE);
+			p.refill_count = kind == SPL_RESET_SPARE_REFILL_NOW ? 1 : (int)(e->n / 2 > 0 ? e->n / 2 : 1);
 		}
 	}
-	int64_t groups = (e->n + 31) / 32;
 	if (e->shuffle_mode == SPL_SHUFFLE_MT19937) {
 		int grid = (int)(groups < (int64_t)g_num_sms * 2 ? groups : (int64_t)g_num_sms * 2);
 		spl_reset_kernel<SPL_SHUFFLE_MT19937><<<grid, 32, SPL_MT_SMEM, st>>>(p);
@@ -1217,7 +1280,7 @@ int spl_reset(const spl_envs_t* envs, const uint64_t* seeds, const uint8_t* rese
 	SPL_CUDA(cudaGetLastError());
 	rc = launch_reset(envs, envs->scratch, seeds, 1, obs, mask, st);
 	if (rc || !spares) return rc;
-	return launch_reset(envs, envs->scratch, nullptr, 0, nullptr, nullptr, st, nullptr, SPL_RESET_SPARE_FILL);
+	return launch_reset(envs, envs->scratch, nullptr, 0, nullptr, nullptr, st, nullptr, SPL_RESET_SPARE_FILL_ENVS);
 }
 
 static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_io_t* io, int32_t* obs, int8_t* mask) {
@@ -1232,6 +1295,7 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.action_t_base = io ? io->action_t_base : nullptr;
 	p.reset_mode = SPL_RESET_NONE;
 	p.spare = e->spare;
+	p.spare_slots = spare_slots(e);
 	if (io && io->autoreset)
 		p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED : (e->spare ? SPL_RESET_SPARE : SPL_RESET_WORKLIST);
 	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;  // 128-bit tile stores
@@ -1363,9 +1427,12 @@ int spl_rollout_random(const spl_envs_t* envs, const spl_step_io_t* io, int32_t 
 	int rc = check_envs(envs);
 	if (rc) return rc;
 	if (!io || !io->actions || !io->reward || !io->terminated || !io->next_action || steps <= 0 || io->active) return SPL_E_BADARG;
-	if (envs->shuffle_mode != SPL_SHUFFLE_PHILOX || !io->autoreset) return SPL_E_BADARG;  // in-kernel resets need the native deal
+	// in-kernel resets need the native deal or, for the reference's own decks, deals prepared ahead of time
+	const bool mt = envs->shuffle_mode == SPL_SHUFFLE_MT19937;
+	if (!io->autoreset || (mt && envs->spare == nullptr) || (!mt && envs->shuffle_mode != SPL_SHUFFLE_PHILOX)) return SPL_E_BADARG;
 	StepParams p;
 	fill_step_params(p, envs, io, io->obs, io->mask);
+	if (mt) p.reset_mode = SPL_RESET_SPARE_INLINE;
 	p.steps = steps;
 	// every step's tile must stay 16-byte aligned: n*297*4 and n*45 are multiples of 16 iff n % 16 == 0
 	if (envs->n % 16 != 0) p.vec_ok = 0;
@@ -1384,7 +1451,10 @@ int spl_rollout_random(const spl_envs_t* envs, const spl_step_io_t* io, int32_t 
 	else spl_rollout_kernel<4><<<L.grid, 128, 0, st>>>(p);
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
 	g_launches++;
-	return (int)cudaGetLastError();
+	SPL_CUDA(cudaGetLastError());
+	// the deals the launch consumed are replaced right behind it (the launch itself never waits for a generator)
+	if (mt) return launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL_NOW);
+	return 0;
 }
 
 int spl_rollout_plan(int64_t n, int32_t steps, int32_t* out) {

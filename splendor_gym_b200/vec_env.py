@@ -67,7 +67,9 @@ class SplendorVecEnv:
     autoreset : same-step auto-reset as in ppo_splendor.py:245-250 (reward/terminated of the finished
         episode, observation/mask of the new one).
     prefetch_deals : with ``shuffle="mt19937"`` and auto-reset, keep the deal of every env's next episode ready
-        (``spl_envs_t.spare``) so that a reset does not wait for ``random.Random(seed)`` on the critical path.
+        (``spl_envs_t.spare``) so that a reset does not wait for ``random.Random(seed)`` on the critical path.  An int
+        S > 1 keeps the next S episodes ready (768 B per env for S = 8): ``rollout_random`` then runs whole segments of
+        up to 17 (S - 1) + 1 lock-steps in ONE launch with the reference's own decks (a game lasts >= 17 moves).
     obs_format : ``"int32"`` = the reference's observation dtype (envs/splendor_env.py:34-36).  ``"f16"`` = policy-ready:
         ``self.obs_f16`` is an fp16 ``[N, 304]`` tensor (entries 0..296 = the observation, exact; 297..303 = 0) that an MLP
         consumes without the cast of ppo_splendor.py:221 and with a 16-byte-aligned K, and ``self.obs`` holds the same
@@ -119,12 +121,14 @@ class SplendorVecEnv:
         self.next_action = torch.zeros(n, dtype=torch.int32, device=d)
         # bit-exact decks with auto-reset: prefetched deal of every env's next episode + refill list (struct spl_envs.spare)
         self.spare = None
+        self.spare_slots = 0
         if self.shuffle_mode == L.SHUFFLE_MT19937 and self.autoreset and prefetch_deals:
-            self.spare = torch.zeros(n * L.DECK_STRIDE + (n + 4) * 4, dtype=torch.uint8, device=d)
+            self.spare_slots = max(1, min(int(prefetch_deals), L.MAX_SPARE_SLOTS))
+            self.spare = torch.zeros(n * self.spare_slots * L.DECK_STRIDE + (n * self.spare_slots + 4) * 4, dtype=torch.uint8, device=d)
         self._envs = L.SplEnvs(
             state=self.state.data_ptr(), decks=self.decks.data_ptr(), episode=self.episode.data_ptr(),
             scratch=self.scratch.data_ptr(), stride=n, n=n, env_offset=int(env_offset), seed_base=int(seed),
-            shuffle_mode=self.shuffle_mode, reserved_=0, spare=None if self.spare is None else self.spare.data_ptr(),
+            shuffle_mode=self.shuffle_mode, spare_slots=self.spare_slots, spare=None if self.spare is None else self.spare.data_ptr(),
         )
         # gymnasium.vector-style attributes (what gym.vector.SyncVectorEnv exposes, ppo_splendor.py:151-159)
         from .envs._gym_compat import spaces
@@ -240,7 +244,8 @@ class SplendorVecEnv:
         auto-reset in ONE kernel launch, streamed into step-major rollout buffers: ``obs [steps,N,297]``,
         ``mask [steps,N,45]``, ``reward / terminated / info [steps,N]``, ``next_actions [steps+1,N]`` (row t+1 = the
         action sampled after step t; row 0 is not written).  ``actions [N]`` are the actions of the first step.
-        Bit-identical to ``steps`` calls of ``step(..., sample_next=True)``.  Needs ``shuffle="philox"`` and autoreset."""
+        Bit-identical to ``steps`` calls of ``step(..., sample_next=True)``.  Needs autoreset and ``shuffle="philox"`` or
+        ``shuffle="mt19937"`` with prefetched deals (``prefetch_deals=8`` for segments of up to 120 lock-steps)."""
         assert self._is_reset, "Call reset() first"
         n = self.n
         assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == n

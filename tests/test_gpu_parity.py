@@ -422,6 +422,80 @@ def test_mt19937_prefetched_deals_bit_exact(VecEnv, oracle, monkeypatch, age, pr
     assert np.array_equal(_np(env.stats), ref.stats()) and int(env.stats[0]) > 2 * n
 
 
+@pytest.mark.parametrize("n,slots,segs", [(2048, 8, (128, 128, 60)), (1000, 1, (90, 40)), (4096 + 48, 3, (150,)), (48, 16, (300,))])
+def test_mt19937_rollout_kernel_bit_exact(VecEnv, oracle, n, slots, segs):
+    """spl_rollout_random with the reference's own decks: shuffle='mt19937' + a ring of prefetched deals per env
+    (spl_envs_t.spare_slots), refilled behind every launch.  Every output of every lock-step equals the oracle's (which
+    deals with CPython's random.Random(seed).shuffle), whatever the ring size: with 8 slots a 128-step launch never runs
+    out, with 1 or 3 slots envs do run out and are dealt in place by the kernel (the slow path)."""
+    env = VecEnv(n, seed=4242, shuffle="mt19937", autoreset=True, prefetch_deals=slots)
+    assert env.spare_slots == slots
+    ref = oracle.OracleVec(n, seed_base=4242)
+    obs0, info0 = env.reset()
+    robs, rmask = ref.reset()
+    assert np.array_equal(_np(obs0), robs) and np.array_equal(_np(info0["action_mask"]), rmask)
+    actions = env.sample_random_actions().clone()
+    t_abs = 0
+    for T in segs:
+        obs = torch.zeros((T, n, 297), dtype=torch.int32, device="cuda")
+        mask = torch.zeros((T, n, 45), dtype=torch.int8, device="cuda")
+        rew = torch.zeros((T, n), dtype=torch.float32, device="cuda")
+        term = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+        info = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+        acts = torch.zeros((T + 1, n), dtype=torch.int32, device="cuda")
+        acts[0] = actions
+        env.rollout_random(T, acts[0], obs=obs, mask=mask, reward=rew, terminated=term, next_actions=acts, info=info)
+        h_obs, h_mask, h_rew, h_term, h_info, h_acts = (_np(x) for x in (obs, mask, rew, term, info, acts))
+        for t in range(T):
+            robs, rrew, rterm, rinfo, rmask = ref.step(h_acts[t], autoreset=True)
+            assert np.array_equal(h_obs[t], robs), f"step {t_abs}: obs"
+            assert np.array_equal(h_mask[t], rmask), f"step {t_abs}: mask"
+            assert np.array_equal(h_rew[t], rrew) and np.array_equal(h_term[t], rterm) and np.array_equal(h_info[t], rinfo), f"step {t_abs}"
+            t_abs += 1
+        actions = acts[T].clone()
+        assert np.array_equal(_np(env.export_state()), ref.export_rows())
+    assert np.array_equal(_np(env.stats), ref.stats()) and int(env.stats[0]) > n
+
+
+def test_mt19937_rollout_then_steps_share_the_ring(VecEnv):
+    """A ring of prefetched deals serves spl_step and spl_rollout_random alike: interleaving them gives the trajectory of
+    plain chained steps without any prefetching (the in-line reset kernel path pinned against the oracle above)."""
+    n = 1024 + 32
+    a = VecEnv(n, seed=6, shuffle="mt19937", autoreset=True, prefetch_deals=4)
+    b = VecEnv(n, seed=6, shuffle="mt19937", autoreset=True, prefetch_deals=False)
+    a.reset()
+    b.reset()
+    actions = a.sample_random_actions().clone()
+    for rep in range(3):
+        T = 50
+        obs = torch.zeros((T, n, 297), dtype=torch.int32, device="cuda")
+        mask = torch.zeros((T, n, 45), dtype=torch.int8, device="cuda")
+        rew = torch.zeros((T, n), dtype=torch.float32, device="cuda")
+        term = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+        acts = torch.zeros((T + 1, n), dtype=torch.int32, device="cuda")
+        acts[0] = actions
+        a.rollout_random(T, acts[0], obs=obs, mask=mask, reward=rew, terminated=term, next_actions=acts)
+        for t in range(T):
+            ob, rb, tb, _, _ = b.step(acts[t].clone(), sample_next=True)
+            assert torch.equal(ob, obs[t]) and torch.equal(b.mask, mask[t]) and torch.equal(rb, rew[t]), f"rep {rep} step {t}"
+            assert torch.equal(b.next_action, acts[t + 1])
+        actions = acts[T].clone()
+        for t in range(40):
+            oa, ra, ta, _, _ = a.step(actions, sample_next=True)
+            ob, rb, tb, _, _ = b.step(actions, sample_next=True)
+            assert torch.equal(oa, ob) and torch.equal(a.mask, b.mask) and torch.equal(ra, rb) and torch.equal(ta, tb), f"rep {rep} step {t}"
+            assert torch.equal(a.next_action, b.next_action)
+            actions = a.next_action.clone()
+        if rep == 1:
+            m = torch.zeros(n, dtype=torch.bool, device="cuda")
+            m[::3] = True
+            a.reset(reset_mask=m)
+            b.reset(reset_mask=m)
+            assert torch.equal(a.obs, b.obs)
+            actions = a.sample_random_actions().clone()
+    assert torch.equal(a.export_state(), b.export_state()) and torch.equal(a.stats, b.stats) and torch.equal(a.episode, b.episode)
+
+
 def test_mt19937_prefetched_deals_survive_manual_resets(VecEnv):
     """Masked manual resets re-deal the chosen envs AND their spares: an env with prefetched deals stays identical to one
     without (the in-line reset path, which the oracle tests pin) through auto-resets, masked resets and a full reset."""

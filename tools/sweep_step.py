@@ -16,9 +16,10 @@ def seg():
         env.step(act[t], out_obs=obs[t], out_mask=mask[t], out_reward=rew[t], out_terminated=term[t], out_next_action=act[t + 1])
     act[0].copy_(act[T]); env.t_base += T
 for spec in sys.argv[2:]:
-    pers, wpc = (spec.split(",") + ["4"])[:2]
+    pers, wpc, order = (spec.split(",") + ["1", "0"])[:3]
     os.environ["SPL_STEP_PERSISTENT"] = pers
     os.environ["SPL_STEP_WPC"] = wpc
+    os.environ["SPL_STEP_ORDER"] = order
     for _ in range(3): seg()
     torch.cuda.synchronize()
     ts = []
@@ -26,4 +27,4 @@ for spec in sys.argv[2:]:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); seg(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     ts.sort(); med = ts[5]
-    print(f"envs={N} persistent={pers} wpc={wpc}: {1e3*med/T:.1f} us per lock-step, {N*T/med/1e6:.3f} G env-steps/s, {N*T*1375/med/1e6:.0f} GB/s", flush=True)
+    print(f"envs={N} persistent={pers} wpc={wpc} order={order}: {1e3*med/T:.1f} us per lock-step, {N*T/med/1e6:.3f} G env-steps/s, {N*T*1375/med/1e6:.0f} GB/s", flush=True)
