@@ -383,6 +383,12 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 			const uint32_t w23 = __shfl_sync(SPL_FULL, wv, 23);  // bytes 92..95: third noble, episode tag (16 bits), ready flag
 			if ((w23 >> 24) == 0u || ((w23 >> 8) & 0xFFFFu) != (ep & 0xFFFFu)) {
 				late |= 1u << src;
+				if (lane == 0) {  // the slot holds nothing usable: have it dealt again (a duplicate entry is harmless)
+					const int idx = atomicAdd(refill, 1);
+					if ((int64_t)idx < p.n * R) refill[4 + idx] = (int32_t)code;
+					const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
+					atomicCAS(reinterpret_cast<unsigned int*>(refill + 1), 0u, (unsigned int)now + 1u);
+				}
 				continue;
 			}
 			if (lane < 24)  // deck row: bytes 90.. are padding there
@@ -392,7 +398,7 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 			if (lane == 23) srow[23] = 0u;  // consumed
 			if (lane == 0) {
 				const int idx = atomicAdd(refill, 1);
-				refill[4 + idx] = (int32_t)code;
+				if ((int64_t)idx < p.n * R) refill[4 + idx] = (int32_t)code;
 				const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
 				atomicCAS(reinterpret_cast<unsigned int*>(refill + 1), 0u, (unsigned int)now + 1u);  // age of the oldest entry
 			}
@@ -728,6 +734,7 @@ struct ResetParams {
 	uint8_t* spare_out;  // non-null: do NOT reset anything; deal upcoming episodes of the listed envs into their spare rows
 	int spare_slots;     // ring slots per env; an item is a code env * slots + slot (refill list / all codes) ...
 	int list_is_envs;    // ... or, for a list of env ids (masked reset), item / slots indexes the list and item % slots is the slot
+	int max_outputs;     // batch dealer: generator outputs a deal may use before it is left to the consumer (227; tests lower it)
 	int32_t* refill;     // with spare_out: the list is the refill list; run only when it is old / long enough, then clear it
 	int refill_age, refill_count;
 };
@@ -864,7 +871,8 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	const int lane = threadIdx.x;
 	const bool spare_mode = SHUFFLE == SPL_SHUFFLE_MT19937 && p.spare_out != nullptr;
 	const int64_t R = spare_mode ? p.spare_slots : 1;
-	const int64_t count = p.list ? (int64_t)p.list[0] * (p.list_is_envs ? R : 1) : p.n * R;
+	int64_t count = p.list ? (int64_t)p.list[0] * (p.list_is_envs ? R : 1) : p.n * R;
+	if (count > p.n * R) count = p.n * R;  // capacity of the lists
 	if (p.refill != nullptr) {  // refill launch (every lock-step): almost always nothing to do yet
 		const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
 		const uint32_t oldest = (uint32_t)p.refill[1];
@@ -981,6 +989,139 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	if (p.refill != nullptr) {  // every CTA read the header before it got here: the last one to arrive empties the list
 		__syncwarp();
 		if (lane == 0) {
+			__threadfence();
+			if (atomicAdd(reinterpret_cast<unsigned int*>(p.refill + 2), 1u) == gridDim.x - 1u) {
+				p.refill[0] = 0, p.refill[1] = 0, p.refill[2] = 0;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batch dealer for the prefetched deals (spl_envs_t.spare): initial_state(seed)'s shuffles for MANY (env, slot) items at
+// once, one item per thread at full occupancy, with the MT19937 generator entirely in REGISTERS.
+//   * random.Random(seed) for a one-word key is two passes over the 624 state words (init_by_array); pass 1 needs no
+//     memory at all (its inputs are the seed-independent init_genrand(19650218) words, a 2.5 KB table), so pass 2 can
+//     re-run pass 1 next to itself instead of reading stored values.
+//   * a deal consumes ~130 outputs, in order, and output k of the first generation is a function of the final words
+//     k, k+1 and k+397 only.  After pass 2 has run once (word 1 is final only at its very end), two more copies of the
+//     pass-2 chain are advanced on demand, one from word 2 and one from word 398 -- every output is produced from
+//     registers, nothing of the state is ever stored.  227 outputs are available that way; a deal that needs more
+//     (never observed in 1e7 games, but rejection sampling can) is left undone: its slot stays "not ready" and the
+//     consumer deals that episode itself (work list / in-place deal).
+//   * the four shuffles run as ONE flat loop per thread (a state machine over (deck, position)): a warp iterates
+//     max-over-lanes of the draws of a whole deal (~155) instead of the sum of per-position maxima (~350) that
+//     32 diverging _randbelow rejection loops would cost.
+// spl_reset_kernel<MT19937> keeps its 624 words per lane in shared memory (2 warps per SM, ~35 us per chain); here
+// ~108,000 deals (what a 65,536-env x 128-step rollout segment consumes) take ~0.1 ms.
+// ------------------------------------------------------------------------------------------------
+#define SPL_DEAL_THREADS 128
+__device__ uint32_t g_mt_init[624];  // init_genrand(19650218): mt[0..623] before init_by_array (spl_init)
+
+struct SplMTChain {  // one copy of the (pass 1, pass 2) recurrences at index i: q = pass-1 word i, p = final word i
+	uint32_t q, p, i;
+	__device__ __forceinline__ uint32_t step(const uint32_t* G, uint32_t key) {
+		i++;
+		q = (G[i] ^ ((q ^ (q >> 30)) * 1664525u)) + key;
+		p = (q ^ ((p ^ (p >> 30)) * 1566083941u)) - i;
+		return p;
+	}
+};
+
+__global__ void __launch_bounds__(SPL_DEAL_THREADS) spl_spare_deal_kernel(const ResetParams p) {
+	__shared__ uint32_t G[624];
+	__shared__ uint8_t decks_s[SPL_DEAL_THREADS * SPL_DECK_SMEM];
+	const int64_t R = p.spare_slots;
+	int64_t count = p.list ? (int64_t)p.list[0] * (p.list_is_envs ? R : 1) : p.n * R;
+	if (count > p.n * R) count = p.n * R;  // capacity of the refill list
+	if (p.refill != nullptr) {  // refill launch of the lock-step path: almost always nothing to do yet
+		const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
+		const uint32_t oldest = (uint32_t)p.refill[1];
+		const bool due = count > 0 && (count >= p.refill_count || (oldest != 0u && (uint32_t)now + 1u - oldest >= (uint32_t)p.refill_age));
+		if (!due) return;
+	}
+	const int64_t tid = (int64_t)blockIdx.x * SPL_DEAL_THREADS + threadIdx.x;
+	if ((int64_t)blockIdx.x * SPL_DEAL_THREADS < count) {
+		for (int k = threadIdx.x; k < 624; k += SPL_DEAL_THREADS) G[k] = g_mt_init[k];
+		__syncthreads();
+	}
+	uint8_t* deck = decks_s + threadIdx.x * SPL_DECK_SMEM;
+	for (int64_t item = tid; item < count; item += (int64_t)gridDim.x * SPL_DEAL_THREADS) {
+		int64_t env, slot;
+		if (p.list != nullptr && p.list_is_envs) env = (int64_t)p.list[4 + item / R], slot = item % R;
+		else {
+			const int64_t code = p.list ? (int64_t)p.list[4 + item] : item;
+			env = code / R, slot = code - env * R;
+		}
+		// the first episode AFTER the current one that lives in this slot; the counter itself moves when a spare is taken
+		const uint32_t cur = p.episode[env];
+		const uint32_t ep = cur + 1u + (uint32_t)(((uint32_t)slot + (uint32_t)R - (cur + 1u) % (uint32_t)R) % (uint32_t)R);
+		const uint32_t key = (uint32_t)((p.seed_base + 1000003ull * ep + p.env_offset + (uint64_t)env) % 2147483647ull);  // one-word key
+		// ---- random.Random(key): init_by_array pass 1 (for its last word), then pass 2 with pass 1 re-run next to it
+		uint32_t q = (G[1] ^ ((G[0] ^ (G[0] >> 30)) * 1664525u)) + key;
+		const uint32_t q1 = q;
+#pragma unroll 8
+		for (int i = 2; i < 624; i++) q = (G[i] ^ ((q ^ (q >> 30)) * 1664525u)) + key;
+		const uint32_t p1 = (q1 ^ ((q ^ (q >> 30)) * 1664525u)) + key;  // 624th iteration: word 1 once more, word 0 <- word 623
+		SplMTChain c;
+		c.q = q1, c.p = p1, c.i = 1;
+#pragma unroll 8
+		for (int i = 2; i <= 397; i++) c.step(G, key);
+		SplMTChain hi = c;  // at word 397
+		const uint32_t mt397 = c.p;
+#pragma unroll 8
+		for (int i = 398; i < 624; i++) c.step(G, key);
+		const uint32_t mt1 = (p1 ^ ((c.p ^ (c.p >> 30)) * 1566083941u)) - 1u;
+		SplMTChain lo;  // at word 1 again: produces words 2, 3, ...
+		lo.q = q1, lo.p = p1, lo.i = 1;
+		// ---- engine/state.py:186-195: shuffle(deck1), shuffle(deck2), shuffle(deck3), shuffle(nobles), Lib/random.py shuffle:
+		// for i in reversed(range(1, len)): j = _randbelow(i + 1); x[i], x[j] = x[j], x[i] -- as one flat loop
+		for (int k = 0; k < 90; k++) deck[k] = (uint8_t)k;
+		for (int k = 0; k < 10; k++) deck[90 + k] = (uint8_t)k;
+		uint32_t a = 0x80000000u, nout = 0;
+		int seg = 0, base = 0, i = 39;
+		bool overflow = false;
+		while (seg < 4) {
+			uint32_t b, cw;
+			if (nout == 0) b = mt1, cw = mt397;
+			else {
+				if (hi.i >= 623u || nout >= (uint32_t)p.max_outputs) {  // output 227 would need the next generation of the state
+					overflow = true;
+					break;
+				}
+				b = lo.step(G, key), cw = hi.step(G, key);
+			}
+			nout++;
+			const uint32_t u = (a & 0x80000000u) | (b & 0x7fffffffu);
+			uint32_t y = cw ^ (u >> 1) ^ ((u & 1u) ? 0x9908b0dfu : 0u);
+			a = b;
+			y ^= y >> 11;
+			y ^= (y << 7) & 0x9d2c5680u;
+			y ^= (y << 15) & 0xefc60000u;
+			y ^= y >> 18;
+			const uint32_t r = y >> (uint32_t)__clz(i + 1);  // getrandbits((i + 1).bit_length())
+			if (r <= (uint32_t)i) {
+				const uint8_t t = deck[base + i];
+				deck[base + i] = deck[base + r];
+				deck[base + r] = t;
+				if (--i < 1) {
+					seg++;
+					base = seg == 1 ? 40 : (seg == 2 ? 70 : 90);
+					i = seg == 1 ? 29 : (seg == 2 ? 19 : 9);
+				}
+			}
+		}
+		if (overflow) continue;
+		// bytes 90..92: the three visible nobles (already there), 93..94: episode tag, 95: ready
+		deck[93] = (uint8_t)(ep & 0xFFu), deck[94] = (uint8_t)((ep >> 8) & 0xFFu), deck[95] = 1;
+		const uint32_t* d4 = reinterpret_cast<const uint32_t*>(deck);
+		uint4* g4 = reinterpret_cast<uint4*>(p.spare_out + (env * R + slot) * SPL_DECK_STRIDE);
+#pragma unroll
+		for (int k = 0; k < SPL_DECK_STRIDE / 16; k++) g4[k] = make_uint4(d4[4 * k], d4[4 * k + 1], d4[4 * k + 2], d4[4 * k + 3]);
+	}
+	if (p.refill != nullptr) {  // every CTA read the header before it got here: the last one to arrive empties the list
+		__syncthreads();
+		if (threadIdx.x == 0) {
 			__threadfence();
 			if (atomicAdd(reinterpret_cast<unsigned int*>(p.refill + 2), 1u) == gridDim.x - 1u) {
 				p.refill[0] = 0, p.refill[1] = 0, p.refill[2] = 0;
@@ -1175,6 +1316,12 @@ int spl_init(void) {
 	}
 	SPL_CUDA(cudaMemcpyToSymbol(g_tables, &T, sizeof(T)));
 	SPL_CUDA(cudaMemcpyToSymbol(g_ret_table, g_host_ret, sizeof(g_host_ret)));
+	{
+		uint32_t g[624];  // Modules/_randommodule.c init_genrand(19650218)
+		g[0] = 19650218u;
+		for (uint32_t i = 1; i < 624; i++) g[i] = 1812433253u * (g[i - 1] ^ (g[i - 1] >> 30)) + i;
+		SPL_CUDA(cudaMemcpyToSymbol(g_mt_init, g, sizeof(g)));
+	}
 	SPL_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
 	SPL_CUDA(cudaFuncSetAttribute(spl_reset_kernel<SPL_SHUFFLE_MT19937>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPL_MT_SMEM));
 	SPL_CUDA(cudaFuncSetAttribute(spl_reset_kernel<SPL_SHUFFLE_PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPL_PHILOX_SMEM));
@@ -1236,7 +1383,7 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 	p.n = e->n, p.env_offset = e->env_offset, p.seed_base = e->seed_base, p.seeds = seeds, p.obs = obs, p.mask = mask;
 	p.bump_episode = bump;
 	p.spare_out = nullptr, p.refill = nullptr, p.refill_age = 0, p.refill_count = 0;
-	p.spare_slots = 1, p.list_is_envs = 0;
+	p.spare_slots = 1, p.list_is_envs = 0, p.max_outputs = env_int("SPL_DEAL_MAX_OUTPUTS", 227);
 	int64_t groups = (e->n + 31) / 32;
 	if (kind != SPL_RESET_NORMAL) {
 		if (e->shuffle_mode != SPL_SHUFFLE_MT19937 || e->spare == nullptr) return SPL_E_BADARG;
@@ -1250,7 +1397,13 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 			p.refill_count = kind == SPL_RESET_SPARE_REFILL_NOW ? 1 : (int)(e->n / 2 > 0 ? e->n / 2 : 1);
 		}
 	}
-	if (e->shuffle_mode == SPL_SHUFFLE_MT19937) {
+	if (kind != SPL_RESET_NORMAL && env_int("SPL_DEAL_BATCH", 1) != 0) {
+		// items: every (env, slot) / every slot of the listed envs / the refill list (length known on the device only)
+		int64_t ctas = (e->n * p.spare_slots + SPL_DEAL_THREADS - 1) / SPL_DEAL_THREADS;
+		const int64_t cap = kind == SPL_RESET_SPARE_REFILL ? g_num_sms : (int64_t)g_num_sms * 12;  // lock-step refills are short lists
+		if (ctas > cap) ctas = cap;
+		spl_spare_deal_kernel<<<(int)ctas, SPL_DEAL_THREADS, 0, st>>>(p);
+	} else if (e->shuffle_mode == SPL_SHUFFLE_MT19937) {
 		int grid = (int)(groups < (int64_t)g_num_sms * 2 ? groups : (int64_t)g_num_sms * 2);
 		spl_reset_kernel<SPL_SHUFFLE_MT19937><<<grid, 32, SPL_MT_SMEM, st>>>(p);
 	} else if (e->shuffle_mode == SPL_SHUFFLE_PHILOX) {

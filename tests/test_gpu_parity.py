@@ -397,16 +397,19 @@ def test_rollout_schedule_independence(VecEnv, monkeypatch, chunk, wpc, ctas_per
     assert int(ref[7][0]) > 0
 
 
-@pytest.mark.parametrize("age,prefetch", [(None, True), ("100000", True), ("1", True), (None, False)])
+@pytest.mark.parametrize("age,prefetch", [(None, True), ("100000", True), ("1", True), (None, False), ("1:130", True), (None, 4)])
 def test_mt19937_prefetched_deals_bit_exact(VecEnv, oracle, monkeypatch, age, prefetch):
     """shuffle='mt19937' with auto-reset takes the prefetched deal of each env's next episode (spl_envs_t.spare) and refills the
     spares in batches.  Whatever the refill cadence -- default, never (every later finish then falls back to the in-line
     reset kernel), every lock-step -- and without spares at all, every output stays bit-identical to the oracle."""
     if age is not None:
+        if ":" in age:  # also hand about half of the deals back to the consumer (see test_mt19937_rollout_kernel_bit_exact)
+            age, max_out = age.split(":")
+            monkeypatch.setenv("SPL_DEAL_MAX_OUTPUTS", max_out)
         monkeypatch.setenv("SPL_SPARE_REFILL_AGE", age)
     n, steps = 2048, 260
     env = VecEnv(n, seed=99, shuffle="mt19937", autoreset=True, prefetch_deals=prefetch)
-    assert (env.spare is not None) == prefetch
+    assert (env.spare is not None) == bool(prefetch)
     ref = oracle.OracleVec(n, seed_base=99)
     obs, info = env.reset()
     robs, rmask = ref.reset()
@@ -422,12 +425,20 @@ def test_mt19937_prefetched_deals_bit_exact(VecEnv, oracle, monkeypatch, age, pr
     assert np.array_equal(_np(env.stats), ref.stats()) and int(env.stats[0]) > 2 * n
 
 
-@pytest.mark.parametrize("n,slots,segs", [(2048, 8, (128, 128, 60)), (1000, 1, (90, 40)), (4096 + 48, 3, (150,)), (48, 16, (300,))])
-def test_mt19937_rollout_kernel_bit_exact(VecEnv, oracle, n, slots, segs):
+@pytest.mark.parametrize("n,slots,segs,max_out", [(2048, 8, (128, 128, 60), None), (1000, 1, (90, 40), None), (4096 + 48, 3, (150,), None),
+                                                   (48, 16, (300,), None), (2048, 8, (128, 100), "128"), (512, 8, (128,), "0"),
+                                                   (2048, 8, (128, 60), "old-kernel")])
+def test_mt19937_rollout_kernel_bit_exact(VecEnv, oracle, monkeypatch, n, slots, segs, max_out):
     """spl_rollout_random with the reference's own decks: shuffle='mt19937' + a ring of prefetched deals per env
     (spl_envs_t.spare_slots), refilled behind every launch.  Every output of every lock-step equals the oracle's (which
     deals with CPython's random.Random(seed).shuffle), whatever the ring size: with 8 slots a 128-step launch never runs
-    out, with 1 or 3 slots envs do run out and are dealt in place by the kernel (the slow path)."""
+    out, with 1 or 3 slots envs do run out and are dealt in place by the kernel (the slow path).  The batch dealer
+    (spl_spare_deal_kernel) leaves a deal to the consumer when it would need more than 227 generator outputs: lowering
+    that limit to 128 (about half of all deals) or 0 (all) exercises the hand-over."""
+    if max_out == "old-kernel":
+        monkeypatch.setenv("SPL_DEAL_BATCH", "0")
+    elif max_out is not None:
+        monkeypatch.setenv("SPL_DEAL_MAX_OUTPUTS", max_out)
     env = VecEnv(n, seed=4242, shuffle="mt19937", autoreset=True, prefetch_deals=slots)
     assert env.spare_slots == slots
     ref = oracle.OracleVec(n, seed_base=4242)
