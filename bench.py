@@ -413,7 +413,8 @@ def run_b200(args):
         del g2
         # the same with the reference's own decks (shuffle="mt19937": every deal bit-identical to initial_state(seed),
         # BASELINE configs[1] "bit-exact replay"); the rollout kernel needs the native Philox deal, this path does not
-        env_mt = SplendorVecEnv(N, device=dev, seed=20261018, shuffle="mt19937", env_offset=rank * N, autoreset=True)
+        env_mt = SplendorVecEnv(N, device=dev, seed=20261018, shuffle="mt19937", env_offset=rank * N, autoreset=True,
+                                prefetch_deals=args.deal_slots)
         env_mt.t_base = env.t_base
         env_mt.reset()
         env_mt.sample_random_actions(out=act_buf[0])
@@ -440,6 +441,37 @@ def run_b200(args):
                                        "what": "same, shuffle=mt19937: decks bit-identical to the reference's initial_state(seed); "
                                                "prefetched next-episode deals (spl_envs_t.spare)"}
         del g3, env_mt
+        if args.shuffle == "philox":
+            # ... and the rollout kernel itself with the reference's decks: a ring of 8 prefetched MT19937 deals per env,
+            # refilled by the batch dealer behind every launch (both inside the timed region)
+            env_mt = SplendorVecEnv(N, device=dev, seed=20261018, shuffle="mt19937", env_offset=rank * N, autoreset=True,
+                                    prefetch_deals=args.deal_slots)
+            env_mt.t_base = env.t_base
+            env_mt.reset()
+            env_mt.sample_random_actions(out=act_buf[0])
+
+            def segment_rollout_mt():
+                env_mt._t = 0
+                env_mt.rollout_random(T, act_buf[0], obs=obs_buf, mask=mask_buf, reward=rew_buf, terminated=term_buf, next_actions=act_buf)
+                act_buf[0].copy_(act_buf[T])
+                env_mt.t_base += T
+
+            for _ in range(3):
+                segment_rollout_mt()
+            k3 = max(3, min(K, 20))
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(k3):
+                segment_rollout_mt()
+            b1.record()
+            torch.cuda.synchronize()
+            rms = b0.elapsed_time(b1)
+            lockstep["rollout_bit_exact_decks"] = {
+                "value": N * T * k3 / (rms * 1e-3), "unit": UNIT, "ms_per_segment": rms / k3,
+                "what": "per-GPU, the rollout kernel (1 launch per %d lock-steps) with shuffle=mt19937: every deal bit-identical to the "
+                        "reference's initial_state(seed), taken from %d prefetched deals per env; the refill (spl_spare_deal_kernel) "
+                        "is inside the timed region" % (T, args.deal_slots)}
+            del env_mt
         env.sample_random_actions(out=act_buf[0])  # back to the Philox env's own action stream
 
     # ---- end-to-end through the public API with HOST buffers: SplendorVecEnv.step_host (C ABI spl_host_step).

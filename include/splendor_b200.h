@@ -132,7 +132,8 @@ typedef struct spl_step_io {
 	                                  the sampler's counter between replays) */
 	int32_t autoreset; /* same-step auto-reset (ppo_splendor.py:245-250) */
 	int32_t reserved_;
-	/* policy-ready observation formats (spl_step only; `obs` must then be NULL and auto-reset needs SPL_SHUFFLE_PHILOX).
+	/* policy-ready observation formats (spl_step only; `obs` must then be NULL and auto-reset needs SPL_SHUFFLE_PHILOX or
+	 * SPL_SHUFFLE_MT19937 with prefetched deals, envs->spare).
 	 * The reference's caller casts the int32 observation to float for the MLP (ppo_splendor.py:221); here the cast is
 	 * fused into the step kernel: */
 	void *obs_f16;   /* [n][SPL_OBS_F16_PITCH] fp16, nullable: entries 0..296 = the observation (exact: all < 256),

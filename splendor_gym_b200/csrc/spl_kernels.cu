@@ -1076,8 +1076,12 @@ __global__ void __launch_bounds__(SPL_DEAL_THREADS) spl_spare_deal_kernel(const 
 		lo.q = q1, lo.p = p1, lo.i = 1;
 		// ---- engine/state.py:186-195: shuffle(deck1), shuffle(deck2), shuffle(deck3), shuffle(nobles), Lib/random.py shuffle:
 		// for i in reversed(range(1, len)): j = _randbelow(i + 1); x[i], x[j] = x[j], x[i] -- as one flat loop
-		for (int k = 0; k < 90; k++) deck[k] = (uint8_t)k;
-		for (int k = 0; k < 10; k++) deck[90 + k] = (uint8_t)k;
+		{  // deck[k] = k for the 90 cards, then the nobles 0..9 at bytes 90..99: 25 word stores
+			uint32_t* dw = reinterpret_cast<uint32_t*>(deck);
+#pragma unroll
+			for (int k = 0; k < 22; k++) dw[k] = 0x03020100u + 0x04040404u * (uint32_t)k;
+			dw[22] = 0x01005958u, dw[23] = 0x05040302u, dw[24] = 0x09080706u;
+		}
 		uint32_t a = 0x80000000u, nout = 0;
 		int seg = 0, base = 0, i = 39;
 		bool overflow = false;
@@ -1368,7 +1372,7 @@ static int env_int(const char* name, int dflt) {
 #define SPL_RESET_SPARE_REFILL 2
 #define SPL_RESET_SPARE_REFILL_NOW 3 /* the refill list, unconditionally (after a rollout launch) */
 #define SPL_RESET_SPARE_FILL_ENVS 4  /* every slot of the envs in a list of env ids (masked reset) */
-#define SPL_SPARE_REFILL_AGE 12 /* lock-steps; a game lasts >= 17 moves, so a spare is back before its env can need it */
+#define SPL_SPARE_REFILL_AGE 16 /* lock-steps per ring slot; a game lasts >= 17 moves, so a deal is back before its env can need it */
 
 static int spare_slots(const spl_envs_t* e) { return e->spare_slots > 1 ? (e->spare_slots > SPL_MAX_SPARE_SLOTS ? SPL_MAX_SPARE_SLOTS : e->spare_slots) : 1; }
 static int32_t* spare_list(const spl_envs_t* e) { return reinterpret_cast<int32_t*>(e->spare + e->n * spare_slots(e) * SPL_DECK_STRIDE); }
@@ -1450,7 +1454,8 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.spare = e->spare;
 	p.spare_slots = spare_slots(e);
 	if (io && io->autoreset)
-		p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED : (e->spare ? SPL_RESET_SPARE : SPL_RESET_WORKLIST);
+		p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED
+		             : (e->spare ? (env_int("SPL_SPARE_WORKLIST", 0) ? SPL_RESET_SPARE : SPL_RESET_SPARE_INLINE) : SPL_RESET_WORKLIST);
 	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;  // 128-bit tile stores
 	p.steps = 1;
 	p.sync = 0;
@@ -1555,9 +1560,12 @@ int spl_step(const spl_envs_t* envs, const spl_step_io_t* io, void* stream) {
 	if (rc) return rc;
 	if (!io || !io->actions || !io->reward || !io->terminated || !io->info) return SPL_E_BADARG;
 	cudaStream_t st = (cudaStream_t)stream;
-	// Philox decks are dealt inside the step kernel; MT19937 decks (bit-exact with the reference) need the
-	// 624-word generator state per env, so finished envs are queued for the reset kernel that follows
-	const bool worklist = io->autoreset && envs->shuffle_mode != SPL_SHUFFLE_PHILOX;
+	// Philox decks are dealt inside the step kernel.  MT19937 decks (bit-exact with the reference) come from the env's
+	// prefetched deals when it has them (spl_envs_t.spare; an env whose ring is empty is dealt in place by one lane of
+	// the step kernel), else finished envs are queued for the reset kernel that follows (624 generator words per env)
+	const bool mt = io->autoreset && envs->shuffle_mode != SPL_SHUFFLE_PHILOX;
+	const bool spares = mt && envs->spare != nullptr;
+	const bool worklist = mt && (!spares || env_int("SPL_SPARE_WORKLIST", 0) != 0);
 	if (worklist) SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, 16, st));
 	if ((io->obs_f16 || io->obs_u8) && worklist) return SPL_E_BADARG;  // the MT19937 reset kernel writes int32 observations only
 	rc = launch_step(envs, io, true, io->obs, io->mask, st, io->obs_f16, io->obs_u8);
@@ -1566,10 +1574,15 @@ int spl_step(const spl_envs_t* envs, const spl_step_io_t* io, void* stream) {
 		// the reset kernel also re-samples next_action for the envs whose mask it replaces
 		rc = launch_reset(envs, envs->scratch, nullptr, 1, io->obs, io->mask, st, io);
 		if (rc) return rc;
-		// prefetched deals: the step kernel took the spares of the envs that finished (the work list above then only
-		// holds the ones that had none); refill them in batches, every SPL_SPARE_REFILL_AGE lock-steps, off the critical path
-		if (envs->spare != nullptr) {
-			rc = launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL);
+	}
+	if (spares) {
+		// the deals the step kernels took are replaced in batches, every (16 x slots)-th lock-step by the caller's lock-step
+		// counter io->action_t: a slot taken at step t is needed again after `slots` more games, i.e. >= 17 x slots moves
+		// later.  The batch costs the latency of one generator chain (~50 us) whatever its size, so a deeper ring makes
+		// the bit-exact lock-step cheaper: 1 slot ~3.5 us per lock-step, 4 slots < 1 us.
+		const int age = env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE * spare_slots(envs));
+		if (age <= 1 || io->action_t % (uint64_t)age == 0) {
+			rc = launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL_NOW);
 			if (rc) return rc;
 		}
 	}

@@ -67,13 +67,14 @@ class SplendorVecEnv:
     autoreset : same-step auto-reset as in ppo_splendor.py:245-250 (reward/terminated of the finished
         episode, observation/mask of the new one).
     prefetch_deals : with ``shuffle="mt19937"`` and auto-reset, keep the deal of every env's next episode ready
-        (``spl_envs_t.spare``) so that a reset does not wait for ``random.Random(seed)`` on the critical path.  An int
-        S > 1 keeps the next S episodes ready (768 B per env for S = 8): ``rollout_random`` then runs whole segments of
+        (``spl_envs_t.spare``) so that a reset does not wait for ``random.Random(seed)`` on the critical path.  ``True`` keeps
+        the next 4 episodes ready (384 B per env; they are replaced in batches every 64 lock-steps), an int S the next S (768 B per env for S = 8): ``rollout_random`` then runs whole segments of
         up to 17 (S - 1) + 1 lock-steps in ONE launch with the reference's own decks (a game lasts >= 17 moves).
     obs_format : ``"int32"`` = the reference's observation dtype (envs/splendor_env.py:34-36).  ``"f16"`` = policy-ready:
         ``self.obs_f16`` is an fp16 ``[N, 304]`` tensor (entries 0..296 = the observation, exact; 297..303 = 0) that an MLP
         consumes without the cast of ppo_splendor.py:221 and with a 16-byte-aligned K, and ``self.obs`` holds the same
-        values as ``uint8 [N, 297]`` (rollout buffers a quarter of the size).  Needs ``shuffle="philox"`` for auto-reset.
+        values as ``uint8 [N, 297]`` (rollout buffers a quarter of the size).  Auto-reset then needs ``shuffle="philox"`` or
+        ``shuffle="mt19937"`` with ``prefetch_deals``.
     """
 
     num_actions = L.NUM_ACTIONS
@@ -104,8 +105,8 @@ class SplendorVecEnv:
             raise ValueError("obs_format must be 'int32' or 'f16'")
         self.obs_format = obs_format
         if obs_format == "f16":
-            if self.autoreset and self.shuffle_mode != L.SHUFFLE_PHILOX:
-                raise L.SplendorB200Error("obs_format='f16' with auto-reset needs shuffle='philox'")
+            if self.autoreset and self.shuffle_mode != L.SHUFFLE_PHILOX and not prefetch_deals:
+                raise L.SplendorB200Error("obs_format='f16' with auto-reset needs shuffle='philox' or prefetched deals")
             self.obs = torch.zeros((n, L.OBS_DIM), dtype=torch.uint8, device=d)
             self.obs_f16 = torch.zeros((n, L.OBS_F16_PITCH), dtype=torch.float16, device=d)
         else:
@@ -123,7 +124,7 @@ class SplendorVecEnv:
         self.spare = None
         self.spare_slots = 0
         if self.shuffle_mode == L.SHUFFLE_MT19937 and self.autoreset and prefetch_deals:
-            self.spare_slots = max(1, min(int(prefetch_deals), L.MAX_SPARE_SLOTS))
+            self.spare_slots = 4 if prefetch_deals is True else max(1, min(int(prefetch_deals), L.MAX_SPARE_SLOTS))
             self.spare = torch.zeros(n * self.spare_slots * L.DECK_STRIDE + (n * self.spare_slots + 4) * 4, dtype=torch.uint8, device=d)
         self._envs = L.SplEnvs(
             state=self.state.data_ptr(), decks=self.decks.data_ptr(), episode=self.episode.data_ptr(),

@@ -349,15 +349,15 @@ def test_step_host_rejects_what_it_cannot_do():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [33, 1000, 4096])
-def test_f16_observation_mode_equals_int32(n):
+@pytest.mark.parametrize("n,shuffle", [(33, "philox"), (1000, "philox"), (4096, "philox"), (1000, "mt19937")])
+def test_f16_observation_mode_equals_int32(n, shuffle):
     """obs_format='f16' (fp16 [N,304] policy input + uint8 observation, cast fused into the step kernel) carries exactly
     the values of the reference-typed int32 observation; masks, rewards, terminations, info and state are unchanged."""
     import torch
     from splendor_gym_b200 import SplendorVecEnv
 
-    a = SplendorVecEnv(n, seed=9, shuffle="philox", autoreset=True)
-    b = SplendorVecEnv(n, seed=9, shuffle="philox", autoreset=True, obs_format="f16")
+    a = SplendorVecEnv(n, seed=9, shuffle=shuffle, autoreset=True)
+    b = SplendorVecEnv(n, seed=9, shuffle=shuffle, autoreset=True, obs_format="f16")
     oa, _ = a.reset()
     ob, _ = b.reset()
 
@@ -396,7 +396,7 @@ def test_f16_mode_argument_checks():
     from splendor_gym_b200._lib import SplendorB200Error
 
     with pytest.raises(SplendorB200Error):
-        SplendorVecEnv(64, shuffle="mt19937", autoreset=True, obs_format="f16")
+        SplendorVecEnv(64, shuffle="mt19937", autoreset=True, obs_format="f16", prefetch_deals=False)
     with pytest.raises(ValueError):
         SplendorVecEnv(64, obs_format="bf16")
     e = SplendorVecEnv(64, seed=3, shuffle="mt19937", autoreset=False, obs_format="f16")  # fine without auto-reset

@@ -397,7 +397,7 @@ def test_rollout_schedule_independence(VecEnv, monkeypatch, chunk, wpc, ctas_per
     assert int(ref[7][0]) > 0
 
 
-@pytest.mark.parametrize("age,prefetch", [(None, True), ("100000", True), ("1", True), (None, False), ("1:130", True), (None, 4)])
+@pytest.mark.parametrize("age,prefetch", [(None, True), ("100000", True), ("1", True), (None, False), ("1:130", True), (None, 1), ("16", 1)])
 def test_mt19937_prefetched_deals_bit_exact(VecEnv, oracle, monkeypatch, age, prefetch):
     """shuffle='mt19937' with auto-reset takes the prefetched deal of each env's next episode (spl_envs_t.spare) and refills the
     spares in batches.  Whatever the refill cadence -- default, never (every later finish then falls back to the in-line
