@@ -1513,6 +1513,17 @@ static LaunchShape launch_shape(int64_t n, int kernel) {
 		}                                                                                    \
 	}
 
+// The deals the step kernels took are replaced in batches, every (16 x slots)-th lock-step by the caller's lock-step
+// counter io->action_t: a slot taken at step t is needed again after `slots` more games, i.e. >= 17 x slots moves later.
+// The batch costs the latency of one generator chain (~50 us) whatever its size, so a deeper ring makes the bit-exact
+// lock-step cheaper: 1 slot ~3.5 us per lock-step, 4 slots < 1 us.
+static int refill_spares_if_due(const spl_envs_t* envs, const spl_step_io_t* io, cudaStream_t st) {
+	const int age = env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE * spare_slots(envs));
+	if (age <= 1 || io->action_t % (uint64_t)age == 0)
+		return launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL_NOW);
+	return 0;
+}
+
 static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, int32_t* obs, int8_t* mask, cudaStream_t st,
                        void* obs_f16 = nullptr, uint8_t* obs_u8 = nullptr) {
 	StepParams p;
@@ -1539,7 +1550,9 @@ static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 int spl_launch_compact(const spl_envs_t* e, const spl_step_io_t* io, bool do_step, uint8_t* obs_u8, void* side, cudaStream_t st) {
 	int rc = check_envs(e);
 	if (rc) return rc;
-	if (e->shuffle_mode != SPL_SHUFFLE_PHILOX && do_step && io && io->autoreset) return SPL_E_BADARG;  // fused reset only
+	// resets must happen inside the step kernel: the native deal, or MT19937 decks with prefetched deals (e->spare)
+	const bool spares = e->shuffle_mode == SPL_SHUFFLE_MT19937 && e->spare != nullptr && do_step && io && io->autoreset;
+	if (e->shuffle_mode != SPL_SHUFFLE_PHILOX && do_step && io && io->autoreset && !spares) return SPL_E_BADARG;
 	StepParams p;
 	fill_step_params(p, e, io, nullptr, nullptr);
 	p.obs_u8 = obs_u8, p.side = (uint4*)side;
@@ -1547,10 +1560,13 @@ int spl_launch_compact(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
+	if (spares) p.reset_mode = SPL_RESET_SPARE_INLINE;
 	SPL_LAUNCH_STEP(SPL_OUT_COMPACT)
 	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
 	g_launches++;
-	return (int)cudaGetLastError();
+	SPL_CUDA(cudaGetLastError());
+	if (spares) return refill_spares_if_due(e, io, st);
+	return 0;
 }
 
 extern "C" {
@@ -1575,17 +1591,7 @@ int spl_step(const spl_envs_t* envs, const spl_step_io_t* io, void* stream) {
 		rc = launch_reset(envs, envs->scratch, nullptr, 1, io->obs, io->mask, st, io);
 		if (rc) return rc;
 	}
-	if (spares) {
-		// the deals the step kernels took are replaced in batches, every (16 x slots)-th lock-step by the caller's lock-step
-		// counter io->action_t: a slot taken at step t is needed again after `slots` more games, i.e. >= 17 x slots moves
-		// later.  The batch costs the latency of one generator chain (~50 us) whatever its size, so a deeper ring makes
-		// the bit-exact lock-step cheaper: 1 slot ~3.5 us per lock-step, 4 slots < 1 us.
-		const int age = env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE * spare_slots(envs));
-		if (age <= 1 || io->action_t % (uint64_t)age == 0) {
-			rc = launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL_NOW);
-			if (rc) return rc;
-		}
-	}
+	if (spares) return refill_spares_if_due(envs, io, st);
 	return 0;
 }
 

@@ -325,9 +325,9 @@ class SplendorVecEnv:
         if obs_dtype not in (torch.int32, torch.uint8):
             raise ValueError("obs_dtype must be torch.int32 or torch.uint8")
         autoreset = self.autoreset if autoreset is None else autoreset
-        if autoreset and self.shuffle_mode != L.SHUFFLE_PHILOX:
-            raise L.SplendorB200Error("step_host with auto-reset needs shuffle='philox' (MT19937 resets run as a second kernel; "
-                                      "use step() and copy, or autoreset=False)")
+        if autoreset and self.shuffle_mode != L.SHUFFLE_PHILOX and self.spare is None:
+            raise L.SplendorB200Error("step_host with auto-reset needs shuffle='philox' or shuffle='mt19937' with prefetch_deals "
+                                      "(resets must happen inside the step kernel)")
         a = torch.as_tensor(actions)
         if a.dtype != torch.int32 or not a.is_contiguous() or a.device.type != "cpu":
             a = a.to(device="cpu", dtype=torch.int32).contiguous()
