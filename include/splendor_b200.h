@@ -163,6 +163,14 @@ int spl_step(const spl_envs_t *envs, const spl_step_io_t *io, void *stream);
  * Requires autoreset and either SPL_SHUFFLE_PHILOX or SPL_SHUFFLE_MT19937 with prefetched deals (envs->spare). */
 int spl_rollout_random(const spl_envs_t *envs, const spl_step_io_t *io, int32_t steps, void *stream);
 
+/* Replace, now, every prefetched deal that has been taken since the last refill (envs->spare, SPL_SHUFFLE_MT19937).
+ * spl_step / spl_host_step do this themselves on every call whose io->action_t is a multiple of 16 x spare_slots (pass
+ * the lock-step counter there), spl_rollout_random behind every launch; a caller that cannot keep that cadence -- e.g.
+ * one that replays a captured single-step CUDA graph, whose action_t is frozen -- calls this every <= 16 x spare_slots
+ * lock-steps instead.  Must be ordered with the step launches (same stream, or an event); an env that finds its ring
+ * empty is dealt in place by the step kernel, bit-identically but slowly (one lane's random.Random(seed), ~35 us). */
+int spl_refill_spares(const spl_envs_t *envs, void *stream);
+
 /* How spl_rollout_random would run `steps` lock-steps of n envs on the current device (measurement aid):
  * out[0] warps per CTA, [1] CTAs, [2] lock-steps per work unit, [3] work units per tile group, [4] CTA barrier per
  * lock-step, [5] tile groups.  Each work unit reloads / stores the packed state of its envs (128 B per env). */

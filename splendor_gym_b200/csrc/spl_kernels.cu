@@ -1629,6 +1629,13 @@ int spl_rollout_random(const spl_envs_t* envs, const spl_step_io_t* io, int32_t 
 	return 0;
 }
 
+int spl_refill_spares(const spl_envs_t* envs, void* stream) {
+	int rc = check_envs(envs);
+	if (rc) return rc;
+	if (envs->shuffle_mode != SPL_SHUFFLE_MT19937 || envs->spare == nullptr) return SPL_E_BADARG;
+	return launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream, nullptr, SPL_RESET_SPARE_REFILL_NOW);
+}
+
 int spl_rollout_plan(int64_t n, int32_t steps, int32_t* out) {
 	if (n <= 0 || steps <= 0 || !out) return SPL_E_BADARG;
 	if (g_inited_device < 0) return SPL_E_NOTINIT;

@@ -266,6 +266,15 @@ class SplendorVecEnv:
             L.check(self.lib.spl_rollout_random(C.byref(self._envs), C.byref(io), int(steps), self._stream()), "spl_rollout_random")
         self._t += steps
 
+    def refill_deals(self) -> None:
+        """Replace every prefetched deal taken since the last refill (``spl_refill_spares``).  ``step`` / ``step_host`` /
+        ``rollout_random`` do this on their own cadence; a caller that replays a captured single-step CUDA graph (whose
+        lock-step counter is frozen) calls it every <= 16 x ``spare_slots`` lock-steps."""
+        if self.spare is None:
+            raise L.SplendorB200Error("refill_deals needs shuffle='mt19937' with prefetch_deals")
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_refill_spares(C.byref(self._envs), self._stream()), "spl_refill_spares")
+
     # ------------------------------------------------------------------ host-buffer API (NumPy-side callers)
     def _host_setup(self, obs_dtype):
         """Host result arrays (reused every call, like gym.vector's pre-allocated observation buffers) + the library's

@@ -507,6 +507,32 @@ def test_mt19937_rollout_then_steps_share_the_ring(VecEnv):
     assert torch.equal(a.export_state(), b.export_state()) and torch.equal(a.stats, b.stats) and torch.equal(a.episode, b.episode)
 
 
+def test_mt19937_manual_refills_with_a_frozen_step_counter(VecEnv, oracle, monkeypatch):
+    """A caller whose io->action_t never reaches the library's refill cadence (a replayed single-step CUDA graph) refills
+    the rings itself with spl_refill_spares; outputs stay those of the oracle and (almost) no env is dealt in place."""
+    monkeypatch.setenv("SPL_SPARE_REFILL_AGE", "1000000")  # the library's own cadence never fires
+    n, steps = 2048, 200
+    env = VecEnv(n, seed=31, shuffle="mt19937", autoreset=True, prefetch_deals=2)
+    ref = oracle.OracleVec(n, seed_base=31)
+    env.reset()
+    ref.reset()
+    actions = env.sample_random_actions().clone()
+    for t in range(steps):
+        a = actions.clone()
+        out = env.step(a, sample_next=True)
+        ref_out = ref.step(_np(a), autoreset=True)
+        assert_step_equal(env, out, ref_out, t)
+        actions = env.next_action.clone()
+        if t % 30 == 29:
+            env.refill_deals()
+            torch.cuda.synchronize()
+            # every slot is ready again: ready byte (95) of each 96-byte row
+            rows = env.spare[: n * 2 * 96].view(n * 2, 96)
+            assert bool((rows[:, 95] == 1).all())
+    assert np.array_equal(_np(env.export_state()), ref.export_rows())
+    assert np.array_equal(_np(env.stats), ref.stats()) and int(env.stats[0]) > n
+
+
 def test_mt19937_prefetched_deals_survive_manual_resets(VecEnv):
     """Masked manual resets re-deal the chosen envs AND their spares: an env with prefetched deals stays identical to one
     without (the in-line reset path, which the oracle tests pin) through auto-resets, masked resets and a full reset."""
