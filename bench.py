@@ -387,7 +387,7 @@ def run_b200(args):
         try:
             with open(prof) as f:
                 tj = json.load(f)
-            key = f"{kernel}:{N}:{T}" + ("" if write_obs else ":noobs")
+            key = f"{kernel}:{N}:{T}" + ("" if write_obs else ":noobs") + (":mt19937" if use_rollout and args.shuffle == "mt19937" else "")
             if key in tj:
                 roofline["traffic"] = tj[key]["dram_bytes_per_launch"]
                 roofline["traffic_source"] = tj[key].get("source")
