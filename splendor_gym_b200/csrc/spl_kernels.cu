@@ -386,8 +386,6 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 				if (lane == 0) {  // the slot holds nothing usable: have it dealt again (a duplicate entry is harmless)
 					const int idx = atomicAdd(refill, 1);
 					if ((int64_t)idx < p.n * R) refill[4 + idx] = (int32_t)code;
-					const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
-					atomicCAS(reinterpret_cast<unsigned int*>(refill + 1), 0u, (unsigned int)now + 1u);
 				}
 				continue;
 			}
@@ -399,8 +397,6 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 			if (lane == 0) {
 				const int idx = atomicAdd(refill, 1);
 				if ((int64_t)idx < p.n * R) refill[4 + idx] = (int32_t)code;
-				const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
-				atomicCAS(reinterpret_cast<unsigned int*>(refill + 1), 0u, (unsigned int)now + 1u);  // age of the oldest entry
 			}
 			if (lane == src) {
 				p.episode[env] = ep;
@@ -735,8 +731,7 @@ struct ResetParams {
 	int spare_slots;     // ring slots per env; an item is a code env * slots + slot (refill list / all codes) ...
 	int list_is_envs;    // ... or, for a list of env ids (masked reset), item / slots indexes the list and item % slots is the slot
 	int max_outputs;     // batch dealer: generator outputs a deal may use before it is left to the consumer (227; tests lower it)
-	int32_t* refill;     // with spare_out: the list is the refill list; run only when it is old / long enough, then clear it
-	int refill_age, refill_count;
+	int32_t* refill;     // with spare_out: the list is the refill list (codes); the last CTA to finish empties it
 };
 
 // MT19937 state of one lane, lane-interleaved in shared memory (conflict-free).  The generator sits on the critical
@@ -873,12 +868,6 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	const int64_t R = spare_mode ? p.spare_slots : 1;
 	int64_t count = p.list ? (int64_t)p.list[0] * (p.list_is_envs ? R : 1) : p.n * R;
 	if (count > p.n * R) count = p.n * R;  // capacity of the lists
-	if (p.refill != nullptr) {  // refill launch (every lock-step): almost always nothing to do yet
-		const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
-		const uint32_t oldest = (uint32_t)p.refill[1];
-		const bool due = count > 0 && (count >= p.refill_count || (oldest != 0u && (uint32_t)now + 1u - oldest >= (uint32_t)p.refill_age));
-		if (!due) return;
-	}
 	if (count == 0) return;
 	spl_stage_tables<32>(T);
 	// A work list (auto-reset of the envs that just finished) is short and sits on the critical path of the lock-step:
@@ -1034,12 +1023,7 @@ __global__ void __launch_bounds__(SPL_DEAL_THREADS) spl_spare_deal_kernel(const 
 	const int64_t R = p.spare_slots;
 	int64_t count = p.list ? (int64_t)p.list[0] * (p.list_is_envs ? R : 1) : p.n * R;
 	if (count > p.n * R) count = p.n * R;  // capacity of the refill list
-	if (p.refill != nullptr) {  // refill launch of the lock-step path: almost always nothing to do yet
-		const uint64_t now = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
-		const uint32_t oldest = (uint32_t)p.refill[1];
-		const bool due = count > 0 && (count >= p.refill_count || (oldest != 0u && (uint32_t)now + 1u - oldest >= (uint32_t)p.refill_age));
-		if (!due) return;
-	}
+	if (count == 0) return;
 	const int64_t tid = (int64_t)blockIdx.x * SPL_DEAL_THREADS + threadIdx.x;
 	if ((int64_t)blockIdx.x * SPL_DEAL_THREADS < count) {
 		for (int k = threadIdx.x; k < 624; k += SPL_DEAL_THREADS) G[k] = g_mt_init[k];
@@ -1365,12 +1349,10 @@ static int env_int(const char* name, int dflt) {
 	return e ? atoi(e) : dflt;
 }
 
-// SPARE_FILL: deal the NEXT episode of the listed envs into their spare rows; SPARE_REFILL: the same for the refill
-// list kept behind the spare rows, run only when the list is old / long enough (decided on the device)
+// what a reset launch does: reset the envs themselves, or (prefetched deals) only deal upcoming episodes into ring slots
 #define SPL_RESET_NORMAL 0
-#define SPL_RESET_SPARE_FILL 1
-#define SPL_RESET_SPARE_REFILL 2
-#define SPL_RESET_SPARE_REFILL_NOW 3 /* the refill list, unconditionally (after a rollout launch) */
+#define SPL_RESET_SPARE_FILL 1 /* every slot of every env (after a full reset) */
+#define SPL_RESET_SPARE_REFILL_NOW 3 /* the refill list (slots taken since the last refill) */
 #define SPL_RESET_SPARE_FILL_ENVS 4  /* every slot of the envs in a list of env ids (masked reset) */
 #define SPL_SPARE_REFILL_AGE 16 /* lock-steps per ring slot; a game lasts >= 17 moves, so a deal is back before its env can need it */
 
@@ -1386,7 +1368,7 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 	p.state = (uint4*)e->state, p.stride = e->stride, p.decks = e->decks, p.episode = e->episode, p.list = list;
 	p.n = e->n, p.env_offset = e->env_offset, p.seed_base = e->seed_base, p.seeds = seeds, p.obs = obs, p.mask = mask;
 	p.bump_episode = bump;
-	p.spare_out = nullptr, p.refill = nullptr, p.refill_age = 0, p.refill_count = 0;
+	p.spare_out = nullptr, p.refill = nullptr;
 	p.spare_slots = 1, p.list_is_envs = 0, p.max_outputs = env_int("SPL_DEAL_MAX_OUTPUTS", 227);
 	int64_t groups = (e->n + 31) / 32;
 	if (kind != SPL_RESET_NORMAL) {
@@ -1395,16 +1377,12 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 		p.spare_slots = spare_slots(e);
 		p.list_is_envs = kind == SPL_RESET_SPARE_FILL_ENVS;
 		groups *= p.spare_slots;
-		if (kind == SPL_RESET_SPARE_REFILL || kind == SPL_RESET_SPARE_REFILL_NOW) {
-			p.list = spare_list(e), p.refill = spare_list(e);
-			p.refill_age = kind == SPL_RESET_SPARE_REFILL_NOW ? 0 : env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE);
-			p.refill_count = kind == SPL_RESET_SPARE_REFILL_NOW ? 1 : (int)(e->n / 2 > 0 ? e->n / 2 : 1);
-		}
+		if (kind == SPL_RESET_SPARE_REFILL_NOW) p.list = spare_list(e), p.refill = spare_list(e);
 	}
 	if (kind != SPL_RESET_NORMAL && env_int("SPL_DEAL_BATCH", 1) != 0) {
 		// items: every (env, slot) / every slot of the listed envs / the refill list (length known on the device only)
 		int64_t ctas = (e->n * p.spare_slots + SPL_DEAL_THREADS - 1) / SPL_DEAL_THREADS;
-		const int64_t cap = kind == SPL_RESET_SPARE_REFILL ? g_num_sms : (int64_t)g_num_sms * 12;  // lock-step refills are short lists
+		const int64_t cap = (int64_t)g_num_sms * 12;
 		if (ctas > cap) ctas = cap;
 		spl_spare_deal_kernel<<<(int)ctas, SPL_DEAL_THREADS, 0, st>>>(p);
 	} else if (e->shuffle_mode == SPL_SHUFFLE_MT19937) {
