@@ -17,9 +17,11 @@
 #if defined(__CUDACC__)
 #define SPL_HD __host__ __device__ __forceinline__
 #define SPL_HD_NOINLINE __host__ __device__ __noinline__
+#define SPL_HD_MEMBER __host__ __device__ __forceinline__
 #else
 #define SPL_HD static inline
 #define SPL_HD_NOINLINE static
+#define SPL_HD_MEMBER inline
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -39,6 +41,14 @@ SPL_HD uint32_t spl_popcll(uint64_t x) {
 	return (uint32_t)__builtin_popcountll(x);
 #endif
 }
+SPL_HD uint32_t spl_clz(uint32_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)__clz((int)x);
+#else
+	return (uint32_t)__builtin_clz(x);
+#endif
+}
+
 SPL_HD uint32_t spl_ffs(uint32_t x) {  // 1-based index of lowest set bit, 0 if none
 #if defined(__CUDA_ARCH__)
 	return __ffs(x);
@@ -345,6 +355,88 @@ SPL_HD_NOINLINE uint64_t spl_mt_top3_block(uint64_t seed, uint32_t blk) {
 		out |= (uint64_t)(v >> 29) << (3 * k);
 	}
 	return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// initial_state(seed)'s four shuffles (engine/state.py:186-195) with CPython's MT19937 held entirely in registers --
+// the per-thread body of the batch dealer (spl_spare_deal_kernel); see the notes there.  `G` = init_genrand(19650218)
+// (624 words, spl_mt_init_table), `key` = the seed as a ONE-word init_by_array key (seeds < 2^32), `deck` = 100 bytes:
+// on return bytes 0..39 / 40..69 / 70..89 hold the shuffled tiers (top of a deck = its end) and 90..99 the shuffled
+// noble ids.  Returns false (deck contents then meaningless) when the deal would need more than min(227, max_outputs)
+// generator outputs: output k of the first generation is a function of the final state words k, k+1, k+397 only, which
+// two restarted copies of the seeding recurrence deliver in order, but output 227 needs the next generation.
+// ------------------------------------------------------------------------------------------------
+SPL_HD void spl_mt_init_table(uint32_t* g) {  // Modules/_randommodule.c init_genrand(19650218)
+	g[0] = 19650218u;
+	for (uint32_t i = 1; i < 624; i++) g[i] = 1812433253u * (g[i - 1] ^ (g[i - 1] >> 30)) + i;
+}
+
+struct SplMTChain {  // one copy of the (pass 1, pass 2) recurrences of init_by_array at index i: q = pass-1 word i, p = final word i
+	uint32_t q, p, i;
+	SPL_HD_MEMBER uint32_t step(const uint32_t* G, uint32_t key) {
+		i++;
+		q = (G[i] ^ ((q ^ (q >> 30)) * 1664525u)) + key;
+		p = (q ^ ((p ^ (p >> 30)) * 1566083941u)) - i;
+		return p;
+	}
+};
+
+SPL_HD bool spl_mt_deal_stream(uint32_t key, const uint32_t* G, uint8_t* deck, uint32_t max_outputs) {
+	// ---- random.Random(key): init_by_array pass 1 (for its last word), then pass 2 with pass 1 re-run next to it
+	uint32_t q = (G[1] ^ ((G[0] ^ (G[0] >> 30)) * 1664525u)) + key;
+	const uint32_t q1 = q;
+#pragma unroll 8
+	for (int i = 2; i < 624; i++) q = (G[i] ^ ((q ^ (q >> 30)) * 1664525u)) + key;
+	const uint32_t p1 = (q1 ^ ((q ^ (q >> 30)) * 1664525u)) + key;  // 624th iteration: word 1 once more, word 0 <- word 623
+	SplMTChain c;
+	c.q = q1, c.p = p1, c.i = 1;
+#pragma unroll 8
+	for (int i = 2; i <= 397; i++) c.step(G, key);
+	SplMTChain hi = c;  // at word 397
+	const uint32_t mt397 = c.p;
+#pragma unroll 8
+	for (int i = 398; i < 624; i++) c.step(G, key);
+	const uint32_t mt1 = (p1 ^ ((c.p ^ (c.p >> 30)) * 1566083941u)) - 1u;
+	SplMTChain lo;  // at word 1 again: produces words 2, 3, ...
+	lo.q = q1, lo.p = p1, lo.i = 1;
+	// ---- shuffle(deck1), shuffle(deck2), shuffle(deck3), shuffle(nobles); Lib/random.py shuffle: for i in
+	// reversed(range(1, len)): j = _randbelow(i + 1); x[i], x[j] = x[j], x[i] -- as ONE flat loop over (deck, position)
+	{  // deck[k] = k for the 90 cards, then the nobles 0..9 at bytes 90..99: 25 word stores
+		uint32_t* dw = reinterpret_cast<uint32_t*>(deck);
+#pragma unroll
+		for (int k = 0; k < 22; k++) dw[k] = 0x03020100u + 0x04040404u * (uint32_t)k;
+		dw[22] = 0x01005958u, dw[23] = 0x05040302u, dw[24] = 0x09080706u;
+	}
+	uint32_t a = 0x80000000u, nout = 0;  // state word 0 after init_by_array
+	int seg = 0, base = 0, i = 39;
+	while (seg < 4) {
+		uint32_t b, cw;
+		if (nout == 0) b = mt1, cw = mt397;
+		else {
+			if (hi.i >= 623u || nout >= max_outputs) return false;
+			b = lo.step(G, key), cw = hi.step(G, key);
+		}
+		nout++;
+		const uint32_t u = (a & 0x80000000u) | (b & 0x7fffffffu);
+		uint32_t y = cw ^ (u >> 1) ^ ((u & 1u) ? 0x9908b0dfu : 0u);
+		a = b;
+		y ^= y >> 11;
+		y ^= (y << 7) & 0x9d2c5680u;
+		y ^= (y << 15) & 0xefc60000u;
+		y ^= y >> 18;
+		const uint32_t r = y >> spl_clz((uint32_t)i + 1u);  // getrandbits((i + 1).bit_length())
+		if (r <= (uint32_t)i) {
+			const uint8_t t = deck[base + i];
+			deck[base + i] = deck[base + r];
+			deck[base + r] = t;
+			if (--i < 1) {
+				seg++;
+				base = seg == 1 ? 40 : (seg == 2 ? 70 : 90);
+				i = seg == 1 ? 29 : (seg == 2 ? 19 : 9);
+			}
+		}
+	}
+	return true;
 }
 
 // auto_return_tokens / _enforce_token_limit (engine/rules.py:150-193) for the mover (index 0).

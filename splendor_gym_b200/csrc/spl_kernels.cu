@@ -1007,16 +1007,6 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 #define SPL_DEAL_THREADS 128
 __device__ uint32_t g_mt_init[624];  // init_genrand(19650218): mt[0..623] before init_by_array (spl_init)
 
-struct SplMTChain {  // one copy of the (pass 1, pass 2) recurrences at index i: q = pass-1 word i, p = final word i
-	uint32_t q, p, i;
-	__device__ __forceinline__ uint32_t step(const uint32_t* G, uint32_t key) {
-		i++;
-		q = (G[i] ^ ((q ^ (q >> 30)) * 1664525u)) + key;
-		p = (q ^ ((p ^ (p >> 30)) * 1566083941u)) - i;
-		return p;
-	}
-};
-
 __global__ void __launch_bounds__(SPL_DEAL_THREADS) spl_spare_deal_kernel(const ResetParams p) {
 	__shared__ uint32_t G[624];
 	__shared__ uint8_t decks_s[SPL_DEAL_THREADS * SPL_DECK_SMEM];
@@ -1041,64 +1031,7 @@ __global__ void __launch_bounds__(SPL_DEAL_THREADS) spl_spare_deal_kernel(const 
 		const uint32_t cur = p.episode[env];
 		const uint32_t ep = cur + 1u + (uint32_t)(((uint32_t)slot + (uint32_t)R - (cur + 1u) % (uint32_t)R) % (uint32_t)R);
 		const uint32_t key = (uint32_t)((p.seed_base + 1000003ull * ep + p.env_offset + (uint64_t)env) % 2147483647ull);  // one-word key
-		// ---- random.Random(key): init_by_array pass 1 (for its last word), then pass 2 with pass 1 re-run next to it
-		uint32_t q = (G[1] ^ ((G[0] ^ (G[0] >> 30)) * 1664525u)) + key;
-		const uint32_t q1 = q;
-#pragma unroll 8
-		for (int i = 2; i < 624; i++) q = (G[i] ^ ((q ^ (q >> 30)) * 1664525u)) + key;
-		const uint32_t p1 = (q1 ^ ((q ^ (q >> 30)) * 1664525u)) + key;  // 624th iteration: word 1 once more, word 0 <- word 623
-		SplMTChain c;
-		c.q = q1, c.p = p1, c.i = 1;
-#pragma unroll 8
-		for (int i = 2; i <= 397; i++) c.step(G, key);
-		SplMTChain hi = c;  // at word 397
-		const uint32_t mt397 = c.p;
-#pragma unroll 8
-		for (int i = 398; i < 624; i++) c.step(G, key);
-		const uint32_t mt1 = (p1 ^ ((c.p ^ (c.p >> 30)) * 1566083941u)) - 1u;
-		SplMTChain lo;  // at word 1 again: produces words 2, 3, ...
-		lo.q = q1, lo.p = p1, lo.i = 1;
-		// ---- engine/state.py:186-195: shuffle(deck1), shuffle(deck2), shuffle(deck3), shuffle(nobles), Lib/random.py shuffle:
-		// for i in reversed(range(1, len)): j = _randbelow(i + 1); x[i], x[j] = x[j], x[i] -- as one flat loop
-		{  // deck[k] = k for the 90 cards, then the nobles 0..9 at bytes 90..99: 25 word stores
-			uint32_t* dw = reinterpret_cast<uint32_t*>(deck);
-#pragma unroll
-			for (int k = 0; k < 22; k++) dw[k] = 0x03020100u + 0x04040404u * (uint32_t)k;
-			dw[22] = 0x01005958u, dw[23] = 0x05040302u, dw[24] = 0x09080706u;
-		}
-		uint32_t a = 0x80000000u, nout = 0;
-		int seg = 0, base = 0, i = 39;
-		bool overflow = false;
-		while (seg < 4) {
-			uint32_t b, cw;
-			if (nout == 0) b = mt1, cw = mt397;
-			else {
-				if (hi.i >= 623u || nout >= (uint32_t)p.max_outputs) {  // output 227 would need the next generation of the state
-					overflow = true;
-					break;
-				}
-				b = lo.step(G, key), cw = hi.step(G, key);
-			}
-			nout++;
-			const uint32_t u = (a & 0x80000000u) | (b & 0x7fffffffu);
-			uint32_t y = cw ^ (u >> 1) ^ ((u & 1u) ? 0x9908b0dfu : 0u);
-			a = b;
-			y ^= y >> 11;
-			y ^= (y << 7) & 0x9d2c5680u;
-			y ^= (y << 15) & 0xefc60000u;
-			y ^= y >> 18;
-			const uint32_t r = y >> (uint32_t)__clz(i + 1);  // getrandbits((i + 1).bit_length())
-			if (r <= (uint32_t)i) {
-				const uint8_t t = deck[base + i];
-				deck[base + i] = deck[base + r];
-				deck[base + r] = t;
-				if (--i < 1) {
-					seg++;
-					base = seg == 1 ? 40 : (seg == 2 ? 70 : 90);
-					i = seg == 1 ? 29 : (seg == 2 ? 19 : 9);
-				}
-			}
-		}
+		const bool overflow = !spl_mt_deal_stream(key, G, deck, (uint32_t)p.max_outputs);
 		if (overflow) continue;
 		// bytes 90..92: the three visible nobles (already there), 93..94: episode tag, 95: ready
 		deck[93] = (uint8_t)(ep & 0xFFu), deck[94] = (uint8_t)((ep >> 8) & 0xFFu), deck[95] = 1;
@@ -1305,9 +1238,8 @@ int spl_init(void) {
 	SPL_CUDA(cudaMemcpyToSymbol(g_tables, &T, sizeof(T)));
 	SPL_CUDA(cudaMemcpyToSymbol(g_ret_table, g_host_ret, sizeof(g_host_ret)));
 	{
-		uint32_t g[624];  // Modules/_randommodule.c init_genrand(19650218)
-		g[0] = 19650218u;
-		for (uint32_t i = 1; i < 624; i++) g[i] = 1812433253u * (g[i - 1] ^ (g[i - 1] >> 30)) + i;
+		uint32_t g[624];
+		spl_mt_init_table(g);
 		SPL_CUDA(cudaMemcpyToSymbol(g_mt_init, g, sizeof(g)));
 	}
 	SPL_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));

@@ -32,6 +32,20 @@ void emu_ret_table(uint64_t* out) {
 
 uint64_t emu_mt_block(uint64_t seed, uint32_t blk) { return spl_mt_top3_block(seed, blk); }
 
+// the batch dealer's per-thread body: initial_state(seed)'s shuffles with the generator in registers
+int emu_mt_deal_stream(uint32_t key, uint8_t* deck100, uint32_t max_outputs) {
+	static uint32_t G[624];
+	static bool have = false;
+	if (!have) {
+		spl_mt_init_table(G);
+		have = true;
+	}
+	alignas(4) uint8_t deck[100];
+	const bool ok = spl_mt_deal_stream(key, G, deck, max_outputs);
+	memcpy(deck100, deck, 100);
+	return ok ? 1 : 0;
+}
+
 // pack -> unpack round trip of a flat row
 void emu_roundtrip(const int32_t* row, int32_t* row_out) {
 	init();

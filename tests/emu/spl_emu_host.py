@@ -53,6 +53,13 @@ def observe(row):
     return obs, mask
 
 
+def mt_deal_stream(key, max_outputs=227):
+    """(ok, deck[100]) of the batch dealer's per-thread body (spl_mt_deal_stream) for a one-word seed."""
+    deck = np.zeros(100, np.uint8)
+    ok = lib().emu_mt_deal_stream(C.c_uint32(int(key)), _p(deck, C.c_uint8), C.c_uint32(int(max_outputs)))
+    return bool(ok), deck
+
+
 def roundtrip(row):
     r = np.ascontiguousarray(row, np.int32)
     out = np.zeros(166, np.int32)

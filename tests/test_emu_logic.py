@@ -29,6 +29,44 @@ def test_mt_block_restatement(oracle):
             assert emu.mt_block(seed, blk) == want, (seed, blk)
 
 
+def _deal_from_row(row):
+    """(tier decks incl. the dealt cards, visible nobles) of a flat state row right after initial_state."""
+    row = list(row)
+    decks = []
+    for t, (off, full) in enumerate(((76, 40), (116, 30), (146, 20))):
+        rest = row[off:off + full - 4]
+        board = row[52 + 4 * t:56 + 4 * t]       # board[t][k] = deck.pop() for k = 0..3 (engine/state.py:190-191)
+        decks.append(rest + board[::-1])
+    return decks, row[67:70]
+
+
+def test_batch_dealer_body_matches_the_reference_deals(oracle):
+    """spl_mt_deal_stream (MT19937 in registers: pass 1 re-run next to pass 2, outputs streamed from two chain copies,
+    one flat shuffle loop) against initial_state(seed) of the reference itself (tests/golden/initial_states.json) and
+    against the oracle for 300 more seeds; the output budget hands a deal back instead of producing a wrong one."""
+    def check(seed, row):
+        ok, deck = emu.mt_deal_stream(seed)
+        assert ok, seed
+        decks, nobles = _deal_from_row(row)
+        assert deck[:40].tolist() == decks[0] and deck[40:70].tolist() == decks[1] and deck[70:90].tolist() == decks[2], seed
+        assert deck[90:93].tolist() == nobles, seed
+
+    for g in load_golden("initial_states.json"):
+        check(g["seed"], g["row"])
+    for base in (0, 123456, 2147483646 - 299):
+        v = oracle.OracleVec(300, seed_base=base)
+        v.reset()
+        rows = v.export_rows()
+        for i in range(300):
+            check((base + i) % 2147483647, rows[i])
+    used = []
+    for seed in range(40):
+        lo = next(m for m in range(90, 228) if emu.mt_deal_stream(seed, m)[0])  # smallest budget that completes the deal
+        assert not emu.mt_deal_stream(seed, lo - 1)[0] and emu.mt_deal_stream(seed, 227)[0]
+        used.append(lo)
+    assert 100 <= min(used) and max(used) <= 200, used  # a deal draws ~130 outputs (96 accepted + rejections)
+
+
 def test_edge_cases_golden():
     for c in load_golden("edge_cases.json"):
         row_in = np.array(c["row_in"], np.int32)
