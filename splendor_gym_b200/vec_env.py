@@ -199,8 +199,14 @@ class SplendorVecEnv:
     def step(self, actions: torch.Tensor, *, active: Optional[torch.Tensor] = None, out_obs: Optional[torch.Tensor] = None,
              out_mask: Optional[torch.Tensor] = None, sample_next: bool = False, autoreset: Optional[bool] = None,
              out_reward: Optional[torch.Tensor] = None, out_terminated: Optional[torch.Tensor] = None,
-             out_next_action: Optional[torch.Tensor] = None, write_obs: bool = True, out_obs_f16: Optional[torch.Tensor] = None):
+             out_next_action: Optional[torch.Tensor] = None, write_obs: bool = True, out_obs_f16: Optional[torch.Tensor] = None,
+             check: bool = False):
         """``SplendorEnv.step`` for every env in lock-step -> (obs, reward, terminated, truncated, info).
+
+        Where the reference raises, the batched step records ``SPL_INFO_ERROR`` in ``info_bits`` and leaves that env
+        untouched; ``check=True`` (one device->host read of the info bytes) raises like the reference does for the
+        first offending env: ``ValueError`` for an action outside ``[0, 45)`` (envs/splendor_env.py:62-63),
+        ``RuntimeError`` for a step after termination (:53-54, only possible without auto-reset).
 
         ``out_obs`` / ``out_mask`` redirect the observation / mask of this step into caller storage (e.g. a
         rollout buffer slice).  ``sample_next`` also draws a uniform random legal action for the returned
@@ -234,6 +240,13 @@ class SplendorVecEnv:
         with torch.cuda.device(self.device):
             L.check(self.lib.spl_step(C.byref(self._envs), C.byref(io), self._stream()), "spl_step")
         self._t += 1
+        if check:
+            bad = torch.nonzero(self.info_bits & L.INFO_ERROR).flatten()
+            if bad.numel():
+                i = int(bad[0])
+                if int(self.info_bits[i]) & L.INFO_TERMINATED:
+                    raise RuntimeError(f"env {i}: step() called on a terminal state ({bad.numel()} envs in error); call reset()")
+                raise ValueError(f"env {i}: action {int(actions[i])} out of range ({bad.numel()} envs in error)")
         if out_reward is not None or out_terminated is not None:
             return obs, reward, term.view(torch.bool), self.truncated, None
         return obs, self.reward, self.terminated, self.truncated, self.info()

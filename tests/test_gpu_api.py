@@ -145,6 +145,35 @@ def test_env_illegal_action_and_errors():
         env.step(0)
 
 
+@pytest.mark.gpu
+def test_vec_env_check_raises_like_the_reference():
+    """Batched error convention: where SplendorEnv.step raises, the lock-step records SPL_INFO_ERROR and leaves
+    the env untouched; check=True turns that into the reference's exceptions."""
+    import torch
+    from splendor_gym_b200 import SplendorVecEnv
+
+    env = SplendorVecEnv(64, seed=3, shuffle="mt19937", autoreset=False)
+    env.reset()
+    a = env.sample_random_actions().clone()
+    env.step(a, check=True)  # legal actions: nothing raised
+    before = env.export_state().clone()
+    a = env.sample_random_actions().clone()
+    a[7] = 45
+    a[9] = -1
+    with pytest.raises(ValueError, match="env 7: action 45"):
+        env.step(a, check=True)
+    after = env.export_state()
+    assert torch.equal(before[7], after[7]) and torch.equal(before[9], after[9])  # untouched, as after the reference's raise
+    # play env 0 to the end without auto-reset, then step it again
+    for _ in range(400):
+        env.step(env.sample_random_actions())
+        if bool(env.terminated.all()):
+            break
+    assert bool(env.terminated.all())
+    with pytest.raises(RuntimeError, match="terminal"):
+        env.step(torch.zeros(64, dtype=torch.int32, device="cuda"), check=True)
+
+
 def test_env_no_legal_move_draw():
     from splendor_gym_b200.engine import legal_moves
     from splendor_gym_b200.envs import SplendorEnv
