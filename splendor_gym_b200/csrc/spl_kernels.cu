@@ -366,11 +366,10 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 	if (p.reset_mode == SPL_RESET_SPARE || p.reset_mode == SPL_RESET_SPARE_INLINE) {
 		// The deals of every env's NEXT episodes were computed ahead of time, off the critical path (one lane's
 		// random.Random(seed) chain takes ~35 us): episode e of an env sits in slot e % slots of its ring, tagged with
-		// e.  Copy it in, mark it consumed and queue the slot for a refill.  A spare that is not there (more finishes of
+		// e.  Copy it in and clear the slot's ready flag (refills find their work by scanning the flags).  A spare that is not there (more finishes of
 		// one env between refills than the ring holds: cannot happen in legal play with the refill cadence used, but
 		// hand-built states may) falls back to the work list below / the in-place deal of the rollout kernel.
 		const int64_t R = p.spare_slots;
-		int32_t* const refill = reinterpret_cast<int32_t*>(p.spare + p.n * R * SPL_DECK_STRIDE);
 		uint32_t late = 0;
 		for (uint32_t todo = rb; todo;) {
 			const int src = __ffs(todo) - 1;
@@ -382,22 +381,14 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 			const uint32_t wv = lane < 24 ? __ldcg(srow + lane) : 0u;
 			const uint32_t w23 = __shfl_sync(SPL_FULL, wv, 23);  // bytes 92..95: third noble, episode tag (16 bits), ready flag
 			if ((w23 >> 24) == 0u || ((w23 >> 8) & 0xFFFFu) != (ep & 0xFFFFu)) {
-				late |= 1u << src;
-				if (lane == 0) {  // the slot holds nothing usable: have it dealt again (a duplicate entry is harmless)
-					const int idx = atomicAdd(refill, 1);
-					if ((int64_t)idx < p.n * R) refill[4 + idx] = (int32_t)code;
-				}
+				late |= 1u << src;  // nothing usable in the slot (the next refill scan finds it by its flag / tag)
 				continue;
 			}
 			if (lane < 24)  // deck row: bytes 90.. are padding there
 				reinterpret_cast<uint32_t*>(p.decks + e * SPL_DECK_STRIDE)[lane] = lane == 22 ? (wv | 0xFFFF0000u) : (lane == 23 ? 0xFFFFFFFFu : wv);
 			const uint32_t w8 = __shfl_sync(SPL_FULL, wv, 8), w9 = __shfl_sync(SPL_FULL, wv, 9), w16 = __shfl_sync(SPL_FULL, wv, 16);
 			const uint32_t w17 = __shfl_sync(SPL_FULL, wv, 17), w21 = __shfl_sync(SPL_FULL, wv, 21), w22 = __shfl_sync(SPL_FULL, wv, 22);
-			if (lane == 23) srow[23] = 0u;  // consumed
-			if (lane == 0) {
-				const int idx = atomicAdd(refill, 1);
-				if ((int64_t)idx < p.n * R) refill[4 + idx] = (int32_t)code;
-			}
+			if (lane == 23) srow[23] = 0u;  // taken: the refill scan (spl_spare_scan_kernel) picks the slot up by this flag
 			if (lane == src) {
 				p.episode[env] = ep;
 				uint32_t board[3];
@@ -986,6 +977,31 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 	}
 }
 
+// Refill scan: which (env, slot) rings entries need a deal?  Those whose ready flag is clear (taken since the last
+// refill, or left undone by the dealer) and those whose tag is not the episode the slot is next needed for (an env that
+// ran its ring dry was dealt in place and has moved past them).  Compacted into the list behind the spare rows; consumers
+// never touch that list, so a scan + deal may run while step kernels take deals from other slots.
+__global__ void __launch_bounds__(256) spl_spare_scan_kernel(const uint8_t* spare, const uint32_t* episode, int64_t n, int slots, int32_t* list) {
+	const int64_t code = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	bool need = false;
+	if (code < n * slots) {
+		const int64_t env = code / slots;
+		const uint32_t slot = (uint32_t)(code - env * slots), R = (uint32_t)slots;
+		const uint32_t w23 = __ldcg(reinterpret_cast<const uint32_t*>(spare + code * SPL_DECK_STRIDE) + 23);
+		const uint32_t cur = __ldcg(episode + env);
+		const uint32_t ep = cur + 1u + (slot + R - (cur + 1u) % R) % R;  // the episode this slot is next needed for
+		need = (w23 >> 24) == 0u || ((w23 >> 8) & 0xFFFFu) != (ep & 0xFFFFu);
+	}
+	const uint32_t b = __ballot_sync(SPL_FULL, need);
+	if (b) {
+		const int lane = threadIdx.x & 31;
+		int base = 0;
+		if (lane == 0) base = atomicAdd(list, __popc(b));
+		base = __shfl_sync(SPL_FULL, base, 0);
+		if (need) list[4 + base + __popc(b & ((1u << lane) - 1u))] = (int32_t)code;
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // Batch dealer for the prefetched deals (spl_envs_t.spare): initial_state(seed)'s shuffles for MANY (env, slot) items at
 // once, one item per thread at full occupancy, with the MT19937 generator entirely in REGISTERS.
@@ -1038,7 +1054,9 @@ __global__ void __launch_bounds__(SPL_DEAL_THREADS) spl_spare_deal_kernel(const 
 		const uint32_t* d4 = reinterpret_cast<const uint32_t*>(deck);
 		uint4* g4 = reinterpret_cast<uint4*>(p.spare_out + (env * R + slot) * SPL_DECK_STRIDE);
 #pragma unroll
-		for (int k = 0; k < SPL_DECK_STRIDE / 16; k++) g4[k] = make_uint4(d4[4 * k], d4[4 * k + 1], d4[4 * k + 2], d4[4 * k + 3]);
+		for (int k = 0; k < SPL_DECK_STRIDE / 16 - 1; k++) g4[k] = make_uint4(d4[4 * k], d4[4 * k + 1], d4[4 * k + 2], d4[4 * k + 3]);
+		__threadfence();  // the last 16 bytes carry the tag and the ready flag: published after the deck order
+		g4[5] = make_uint4(d4[20], d4[21], d4[22], d4[23]);
 	}
 	if (p.refill != nullptr) {  // every CTA read the header before it got here: the last one to arrive empties the list
 		__syncthreads();
@@ -1309,7 +1327,14 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 		p.spare_slots = spare_slots(e);
 		p.list_is_envs = kind == SPL_RESET_SPARE_FILL_ENVS;
 		groups *= p.spare_slots;
-		if (kind == SPL_RESET_SPARE_REFILL_NOW) p.list = spare_list(e), p.refill = spare_list(e);
+		if (kind == SPL_RESET_SPARE_REFILL_NOW) {  // build the list of slots to deal: scan the ready flags / tags
+			p.list = spare_list(e), p.refill = spare_list(e);
+			SPL_CUDA(cudaMemsetAsync(spare_list(e), 0, 16, st));
+			const int64_t codes = e->n * p.spare_slots;
+			spl_spare_scan_kernel<<<(unsigned)((codes + 255) / 256), 256, 0, st>>>(e->spare, e->episode, e->n, p.spare_slots, spare_list(e));
+			g_launches++;
+			SPL_CUDA(cudaGetLastError());
+		}
 	}
 	if (kind != SPL_RESET_NORMAL && env_int("SPL_DEAL_BATCH", 1) != 0) {
 		// items: every (env, slot) / every slot of the listed envs / the refill list (length known on the device only)
