@@ -456,16 +456,19 @@ def run_b200(args):
                 act_buf[0].copy_(act_buf[T])
                 env_mt.t_base += T
 
-            for _ in range(3):
-                segment_rollout_mt()
+            def timed(fn, reps):
+                for _ in range(3):
+                    fn()
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                for _ in range(reps):
+                    fn()
+                b1.record()
+                torch.cuda.synchronize()
+                return b0.elapsed_time(b1)
+
             k3 = max(3, min(K, 20))
-            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            b0.record()
-            for _ in range(k3):
-                segment_rollout_mt()
-            b1.record()
-            torch.cuda.synchronize()
-            rms = b0.elapsed_time(b1)
+            rms = timed(segment_rollout_mt, k3)
             lockstep["rollout_bit_exact_decks"] = {
                 "value": N * T * k3 / (rms * 1e-3), "unit": UNIT, "ms_per_segment": rms / k3,
                 "what": "per-GPU, the rollout kernel (1 launch per %d lock-steps) with shuffle=mt19937: every deal bit-identical to the "

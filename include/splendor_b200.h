@@ -115,6 +115,13 @@ typedef struct spl_envs {
 	                        (an env that runs out is dealt in place, slowly).  Zero it once. */
 } spl_envs_t;
 
+/* spl_step_io.flags */
+#define SPL_IO_ASYNC_REFILL 1 /* prefetched deals (envs->spare): this call does not refill the rings; the caller runs
+                                 spl_refill_spares itself -- possibly on another stream, CONCURRENTLY with later step /
+                                 rollout launches that carry this flag (they then read a slot's ready flag before its
+                                 deck order).  The refill of the deals taken by launch k must have completed before launch
+                                 k + 2 starts if no env is to run its ring dry (16 slots cover two 128-step launches). */
+
 /* Outputs of one lock-step (the 5-tuple of SplendorEnv.step, batched). Nullable members are skipped. */
 typedef struct spl_step_io {
 	const int32_t *actions; /* [n] */
@@ -131,7 +138,7 @@ typedef struct spl_step_io {
 	const uint64_t *action_t_base; /* nullable device scalar added to action_t (lets a captured CUDA graph advance
 	                                  the sampler's counter between replays) */
 	int32_t autoreset; /* same-step auto-reset (ppo_splendor.py:245-250) */
-	int32_t reserved_;
+	int32_t flags;     /* SPL_IO_* */
 	/* policy-ready observation formats (spl_step only; `obs` must then be NULL and auto-reset needs SPL_SHUFFLE_PHILOX or
 	 * SPL_SHUFFLE_MT19937 with prefetched deals, envs->spare).
 	 * The reference's caller casts the int32 observation to float for the MLP (ppo_splendor.py:221); here the cast is
@@ -167,8 +174,9 @@ int spl_rollout_random(const spl_envs_t *envs, const spl_step_io_t *io, int32_t 
  * spl_step / spl_host_step do this themselves on every call whose io->action_t is a multiple of 16 x spare_slots (pass
  * the lock-step counter there), spl_rollout_random behind every launch; a caller that cannot keep that cadence -- e.g.
  * one that replays a captured single-step CUDA graph, whose action_t is frozen -- calls this every <= 16 x spare_slots
- * lock-steps instead.  Must be ordered with the step launches (same stream, or an event); an env that finds its ring
- * empty is dealt in place by the step kernel, bit-identically but slowly (one lane's random.Random(seed), ~35 us). */
+ * lock-steps instead.  It may run concurrently with step / rollout launches that carry SPL_IO_ASYNC_REFILL (the rows are
+ * published flag-last and taken flag-first); otherwise order it with them (same stream, or an event).  An env that finds
+ * its ring empty is dealt in place by the step kernel, bit-identically but slowly (one lane's random.Random(seed), ~35 us). */
 int spl_refill_spares(const spl_envs_t *envs, void *stream);
 
 /* How spl_rollout_random would run `steps` lock-steps of n envs on the current device (measurement aid):

@@ -19,6 +19,7 @@ STATE_PLANES = 4
 DECK_STRIDE = 96
 RET_TABLE_LEN = 8910
 MAX_SPARE_SLOTS = 16
+IO_ASYNC_REFILL = 1
 
 INFO_ILLEGAL = 1
 INFO_NOLEGAL_DRAW = 2
@@ -62,7 +63,7 @@ class SplStepIO(C.Structure):
         ("actions", C.c_void_p), ("active", C.c_void_p), ("obs", C.c_void_p), ("mask", C.c_void_p),
         ("reward", C.c_void_p), ("terminated", C.c_void_p), ("info", C.c_void_p), ("stats", C.c_void_p),
         ("next_action", C.c_void_p), ("action_key", C.c_uint64), ("action_t", C.c_uint64),
-        ("action_t_base", C.c_void_p), ("autoreset", C.c_int32), ("reserved_", C.c_int32),
+        ("action_t_base", C.c_void_p), ("autoreset", C.c_int32), ("flags", C.c_int32),
         ("obs_f16", C.c_void_p), ("obs_u8", C.c_void_p),
     ]
 

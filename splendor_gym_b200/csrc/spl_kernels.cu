@@ -309,6 +309,7 @@ struct StepParams {
 	int reset_mode;
 	uint8_t* spare;      // SPL_RESET_SPARE: [n][slots][96] prefetched deals, then the int32 refill list (header of 4 + n*slots entries)
 	int spare_slots;     // deals kept ahead per env (ring indexed by episode % slots)
+	int spare_async;     // a refill may be dealing into the ring while this launch runs: read a slot's flag word first (acquire)
 	int vec_ok;  // obs / mask bases are 16-byte aligned (and, for step-major buffers, every step's slice is)
 	int steps;   // rollout kernel: lock-steps per launch; outputs are [steps][n][...], next_action is [steps+1][n]
 	int sync;    // rollout kernel: CTA barrier per lock-step (keeps the warps of a CTA in the same code region)
@@ -325,6 +326,12 @@ struct SplTile {
 	int64_t ti;      // tile index; env = ti*32 + lane
 	int rows;        // valid envs in the tile
 };
+
+__device__ __forceinline__ uint32_t spl_ld_acquire(const uint32_t* p) {
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
 
 // initial_state(seed) by ONE lane, MT19937 state in `smem` (>= 656 words), deck row to global memory (defined below);
 // results in smem[648..652]: board rows, visible nobles, deck tops (no reference arguments: nothing of the caller is
@@ -378,8 +385,15 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 			const uint32_t ep = __ldcg(p.episode + e) + 1u;  // the episode that starts now (L2: another SM may have bumped it)
 			const int64_t code = e * R + (int64_t)(ep % (uint32_t)R);
 			uint32_t* srow = reinterpret_cast<uint32_t*>(p.spare + code * SPL_DECK_STRIDE);
+			// bytes 92..95 of the row: third noble, episode tag (16 bits), ready flag.  The dealer publishes them last, so when
+			// a refill may be running concurrently they are read first, with acquire semantics, and the deck order after
+			uint32_t w23 = p.spare_async ? spl_ld_acquire(srow + 23) : 0u;
+			if (p.spare_async && ((w23 >> 24) == 0u || ((w23 >> 8) & 0xFFFFu) != (ep & 0xFFFFu))) {
+				late |= 1u << src;
+				continue;
+			}
 			const uint32_t wv = lane < 24 ? __ldcg(srow + lane) : 0u;
-			const uint32_t w23 = __shfl_sync(SPL_FULL, wv, 23);  // bytes 92..95: third noble, episode tag (16 bits), ready flag
+			if (!p.spare_async) w23 = __shfl_sync(SPL_FULL, wv, 23);
 			if ((w23 >> 24) == 0u || ((w23 >> 8) & 0xFFFFu) != (ep & 0xFFFFu)) {
 				late |= 1u << src;  // nothing usable in the slot (the next refill scan finds it by its flag / tag)
 				continue;
@@ -594,12 +608,6 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 // Chunk lengths: `chunk` lock-steps each, then the last chunk..2*chunk steps are halved down to 2 so that the
 // tail of the launch (CTAs finding the queue empty) is short.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t spl_ld_acquire(const uint32_t* p) {
-	uint32_t v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-
 __device__ __forceinline__ void spl_st_release(uint32_t* p, uint32_t v) {
 	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -1388,6 +1396,7 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.reset_mode = SPL_RESET_NONE;
 	p.spare = e->spare;
 	p.spare_slots = spare_slots(e);
+	p.spare_async = io && (io->flags & SPL_IO_ASYNC_REFILL) ? 1 : 0;
 	if (io && io->autoreset)
 		p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED
 		             : (e->spare ? (env_int("SPL_SPARE_WORKLIST", 0) ? SPL_RESET_SPARE : SPL_RESET_SPARE_INLINE) : SPL_RESET_WORKLIST);
@@ -1453,6 +1462,7 @@ static LaunchShape launch_shape(int64_t n, int kernel) {
 // The batch costs the latency of one generator chain (~50 us) whatever its size, so a deeper ring makes the bit-exact
 // lock-step cheaper: 1 slot ~3.5 us per lock-step, 4 slots < 1 us.
 static int refill_spares_if_due(const spl_envs_t* envs, const spl_step_io_t* io, cudaStream_t st) {
+	if (io->flags & SPL_IO_ASYNC_REFILL) return 0;  // the caller refills (spl_refill_spares)
 	const int age = env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE * spare_slots(envs));
 	if (age <= 1 || io->action_t % (uint64_t)age == 0)
 		return launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL_NOW);
@@ -1560,7 +1570,7 @@ int spl_rollout_random(const spl_envs_t* envs, const spl_step_io_t* io, int32_t 
 	g_launches++;
 	SPL_CUDA(cudaGetLastError());
 	// the deals the launch consumed are replaced right behind it (the launch itself never waits for a generator)
-	if (mt) return launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL_NOW);
+	if (mt && !(io->flags & SPL_IO_ASYNC_REFILL)) return launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL_NOW);
 	return 0;
 }
 

@@ -253,13 +253,16 @@ class SplendorVecEnv:
 
     def rollout_random(self, steps: int, actions: torch.Tensor, *, obs: Optional[torch.Tensor], mask: Optional[torch.Tensor],
                        reward: torch.Tensor, terminated: torch.Tensor, next_actions: torch.Tensor,
-                       info: Optional[torch.Tensor] = None) -> None:
+                       info: Optional[torch.Tensor] = None, refill: bool = True) -> None:
         """``steps`` lock-steps of uniform-random-legal play (scripts/random_rollout.py:13-30, batched) with same-step
         auto-reset in ONE kernel launch, streamed into step-major rollout buffers: ``obs [steps,N,297]``,
         ``mask [steps,N,45]``, ``reward / terminated / info [steps,N]``, ``next_actions [steps+1,N]`` (row t+1 = the
         action sampled after step t; row 0 is not written).  ``actions [N]`` are the actions of the first step.
         Bit-identical to ``steps`` calls of ``step(..., sample_next=True)``.  Needs autoreset and ``shuffle="philox"`` or
-        ``shuffle="mt19937"`` with prefetched deals (``prefetch_deals=8`` for segments of up to 120 lock-steps)."""
+        ``shuffle="mt19937"`` with prefetched deals (``prefetch_deals=8`` for segments of up to 120 lock-steps).
+        ``refill=False`` (MT19937): the launch does not replace the deals it takes; the caller runs ``refill_deals()``,
+        typically on a side stream while the NEXT segment is already running (``prefetch_deals=16`` then covers the two
+        segments in flight), and makes launch k+2 wait for the refill that followed launch k."""
         assert self._is_reset, "Call reset() first"
         n = self.n
         assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.numel() == n
@@ -275,14 +278,19 @@ class SplendorVecEnv:
         io.action_key, io.action_t = self.action_key, self._t + 1
         io.action_t_base = _ptr(self.t_base)
         io.autoreset = 1
-        with torch.cuda.device(self.device):
-            L.check(self.lib.spl_rollout_random(C.byref(self._envs), C.byref(io), int(steps), self._stream()), "spl_rollout_random")
+        io.flags = 0 if refill else L.IO_ASYNC_REFILL
+        try:
+            with torch.cuda.device(self.device):
+                L.check(self.lib.spl_rollout_random(C.byref(self._envs), C.byref(io), int(steps), self._stream()), "spl_rollout_random")
+        finally:
+            io.flags = 0
         self._t += steps
 
     def refill_deals(self) -> None:
         """Replace every prefetched deal taken since the last refill (``spl_refill_spares``).  ``step`` / ``step_host`` /
         ``rollout_random`` do this on their own cadence; a caller that replays a captured single-step CUDA graph (whose
-        lock-step counter is frozen) calls it every <= 16 x ``spare_slots`` lock-steps."""
+        lock-step counter is frozen) calls it every <= 16 x ``spare_slots`` lock-steps.  Runs on the current torch stream:
+        inside ``with torch.cuda.stream(side)`` it overlaps ``rollout_random(..., refill=False)`` launches on the main one."""
         if self.spare is None:
             raise L.SplendorB200Error("refill_deals needs shuffle='mt19937' with prefetch_deals")
         with torch.cuda.device(self.device):

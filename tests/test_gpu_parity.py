@@ -468,6 +468,56 @@ def test_mt19937_rollout_kernel_bit_exact(VecEnv, oracle, monkeypatch, n, slots,
     assert np.array_equal(_np(env.stats), ref.stats()) and int(env.stats[0]) > n
 
 
+@pytest.mark.parametrize("n,slots,T,segs", [(16384, 16, 64, 8), (16384, 2, 64, 8), (4096, 1, 40, 10)])
+def test_mt19937_rollout_with_concurrent_refills(VecEnv, oracle, n, slots, T, segs):
+    """rollout_random(refill=False) launches back to back on the main stream while refill_deals() runs on a side stream
+    (scan + batch dealer concurrently with the NEXT launch).  The dealer publishes a row flag-last, the consumer reads the
+    flag first; with 16 slots no env ever runs dry, with 1 or 2 the rings do run dry while they are being refilled -- envs
+    are then dealt in place, slots end up with stale tags and are re-dealt by a later scan.  Whatever the interleaving,
+    every output equals the oracle's."""
+    env = VecEnv(n, seed=777, shuffle="mt19937", autoreset=True, prefetch_deals=slots)
+    ref = oracle.OracleVec(n, seed_base=777)
+    env.reset()
+    ref.reset()
+    TT = T * segs
+    obs = torch.zeros((TT, n, 297), dtype=torch.int32, device="cuda")
+    mask = torch.zeros((TT, n, 45), dtype=torch.int8, device="cuda")
+    rew = torch.zeros((TT, n), dtype=torch.float32, device="cuda")
+    term = torch.zeros((TT, n), dtype=torch.uint8, device="cuda")
+    info = torch.zeros((TT, n), dtype=torch.uint8, device="cuda")
+    acts = torch.zeros((TT + 1, n), dtype=torch.int32, device="cuda")
+    acts[0] = env.sample_random_actions()
+    side = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    pending = []
+    for k in range(segs):  # no host synchronisation inside this loop
+        if len(pending) >= 2:
+            main.wait_event(pending[-2])
+        lo, hi = k * T, (k + 1) * T
+        env.rollout_random(T, acts[lo], obs=obs[lo:hi], mask=mask[lo:hi], reward=rew[lo:hi], terminated=term[lo:hi],
+                           next_actions=acts[lo:hi + 1], info=info[lo:hi], refill=False)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            env.refill_deals()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        pending.append(ev)
+    main.wait_stream(side)
+    torch.cuda.synchronize()
+    h_obs, h_mask, h_rew, h_term, h_info, h_acts = (_np(x) for x in (obs, mask, rew, term, info, acts))
+    for t in range(TT):
+        robs, rrew, rterm, rinfo, rmask = ref.step(h_acts[t], autoreset=True)
+        assert np.array_equal(h_obs[t], robs), f"step {t}: obs"
+        assert np.array_equal(h_mask[t], rmask), f"step {t}: mask"
+        assert np.array_equal(h_rew[t], rrew) and np.array_equal(h_term[t], rterm) and np.array_equal(h_info[t], rinfo), f"step {t}"
+    assert np.array_equal(_np(env.export_state()), ref.export_rows())
+    assert np.array_equal(_np(env.stats), ref.stats()) and int(env.stats[0]) > n
+    env.refill_deals()
+    torch.cuda.synchronize()
+    rows = env.spare[: n * slots * 96].view(n * slots, 96)
+    assert bool((rows[:, 95] == 1).all())  # every slot ready again
+
+
 def test_mt19937_rollout_then_steps_share_the_ring(VecEnv):
     """A ring of prefetched deals serves spl_step and spl_rollout_random alike: interleaving them gives the trajectory of
     plain chained steps without any prefetching (the in-line reset kernel path pinned against the oracle above)."""

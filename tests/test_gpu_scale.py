@@ -59,7 +59,8 @@ def test_parity_volume(oracle):
             f.write(msg + "\n")
 
 
-def test_parity_volume_rollout_kernel(oracle):
+@pytest.mark.parametrize("async_refill", [False, True])
+def test_parity_volume_rollout_kernel(oracle, async_refill):
     """The same volume through spl_rollout_random with the reference's own decks (shuffle='mt19937', ring of 8 prefetched
     deals per env, batch dealer behind every 128-step launch): every observation, mask, reward, termination and info
     byte of every lock-step against the oracle, which deals with CPython's random.Random(seed).shuffle."""
@@ -68,9 +69,13 @@ def test_parity_volume_rollout_kernel(oracle):
     from splendor_gym_b200 import SplendorVecEnv
 
     target = int(os.environ.get("SPL_SCALE_GAMES_ROLLOUT", os.environ.get("SPL_SCALE_GAMES", "1000000")))
+    if async_refill:  # refills on a side stream while the next launch runs (two launches in flight before the checks)
+        target //= 4
     n, T = 65536, 128
     dev = torch.device("cuda")
-    env = SplendorVecEnv(n, seed=4321, shuffle="mt19937", autoreset=True, prefetch_deals=8)
+    env = SplendorVecEnv(n, seed=4321, shuffle="mt19937", autoreset=True, prefetch_deals=16 if async_refill else 8)
+    side = torch.cuda.Stream()
+    pending = []
     ref = oracle.OracleVec(n, seed_base=4321)
     obs0, _ = env.reset()
     robs, _ = ref.reset()
@@ -86,7 +91,21 @@ def test_parity_volume_rollout_kernel(oracle):
     steps = 0
     games = 0
     while games < target:
-        env.rollout_random(T, acts[0], obs=obs, mask=mask, reward=rew, terminated=term, next_actions=acts, info=info)
+        if async_refill:
+            # the deals this launch takes are replaced on the side stream WHILE the host checks run and -- because the
+            # wait is for the refill before last -- while the next launch runs
+            main = torch.cuda.current_stream()
+            if len(pending) >= 2:
+                main.wait_event(pending[-2])
+            env.rollout_random(T, acts[0], obs=obs, mask=mask, reward=rew, terminated=term, next_actions=acts, info=info, refill=False)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                env.refill_deals()
+                ev = torch.cuda.Event()
+                ev.record(side)
+            pending.append(ev)
+        else:
+            env.rollout_random(T, acts[0], obs=obs, mask=mask, reward=rew, terminated=term, next_actions=acts, info=info)
         h_acts = acts.cpu().numpy()
         h_small = [x.cpu().numpy() for x in (rew, term, info)]
         for t in range(T):
@@ -101,7 +120,8 @@ def test_parity_volume_rollout_kernel(oracle):
         games = int(ref.stats()[0])
     assert np.array_equal(env.stats.cpu().numpy(), ref.stats())
     st = ref.stats()
-    msg = (f"parity volume (rollout kernel, MT19937 decks): {games} games, {steps} lock-steps x {n} envs = {steps * n} env-steps "
+    torch.cuda.synchronize()
+    msg = (f"parity volume (rollout kernel, MT19937 decks{', refills on a side stream' if async_refill else ''}): {games} games, {steps} lock-steps x {n} envs = {steps * n} env-steps "
            f"bit-exact (p0 {st[1]}, p1 {st[2]}, ties {st[3]}, limit {st[4]}, no-legal {st[5]}) in {time.time() - t0:.1f} s")
     print(msg)
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
