@@ -171,8 +171,8 @@ int spl_step(const spl_envs_t *envs, const spl_step_io_t *io, void *stream);
 int spl_rollout_random(const spl_envs_t *envs, const spl_step_io_t *io, int32_t steps, void *stream);
 
 /* Replace, now, every prefetched deal that has been taken since the last refill (envs->spare, SPL_SHUFFLE_MT19937).
- * spl_step / spl_host_step do this themselves on every call whose io->action_t is a multiple of 16 x spare_slots (pass
- * the lock-step counter there), spl_rollout_random behind every launch; a caller that cannot keep that cadence -- e.g.
+ * spl_step / spl_host_step do this themselves on every call whose io->action_t is a multiple of 16 x min(spare_slots, 4)
+ * (pass the lock-step counter there), spl_rollout_random behind every launch; a caller that cannot keep that cadence -- e.g.
  * one that replays a captured single-step CUDA graph, whose action_t is frozen -- calls this every <= 16 x spare_slots
  * lock-steps instead.  It may run concurrently with step / rollout launches that carry SPL_IO_ASYNC_REFILL (the rows are
  * published flag-last and taken flag-first); otherwise order it with them (same stream, or an event).  An env that finds

@@ -1463,7 +1463,10 @@ static LaunchShape launch_shape(int64_t n, int kernel) {
 // lock-step cheaper: 1 slot ~3.5 us per lock-step, 4 slots < 1 us.
 static int refill_spares_if_due(const spl_envs_t* envs, const spl_step_io_t* io, cudaStream_t st) {
 	if (io->flags & SPL_IO_ASYNC_REFILL) return 0;  // the caller refills (spl_refill_spares)
-	const int age = env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE * spare_slots(envs));
+	// (capped at 64 lock-steps: callers that re-base action_t per rollout segment, e.g. per replayed CUDA graph, then still
+	// reach the cadence inside every segment of 64 x k lock-steps)
+	const int slots = spare_slots(envs) < 4 ? spare_slots(envs) : 4;
+	const int age = env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE * slots);
 	if (age <= 1 || io->action_t % (uint64_t)age == 0)
 		return launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL_NOW);
 	return 0;
