@@ -103,6 +103,8 @@ def main(argv=None):
     ap.add_argument("--bf16", action="store_true")
     ap.add_argument("--obs-format", default="int32", choices=["int32", "f16"],
                     help="f16: the step kernel emits the fp16 [N,304] policy input itself (policy runs in fp16, padded layers)")
+    ap.add_argument("--shuffle", default="philox", choices=["philox", "mt19937"],
+                    help="mt19937: every deal bit-identical to the reference's initial_state(seed) (prefetched deals)")
     ap.add_argument("--repeats", type=int, default=2)
     args = ap.parse_args(argv)
     torch.manual_seed(args.seed)
@@ -114,7 +116,7 @@ def main(argv=None):
     net = net.to(dtype).eval()
     if args.obs_format == "f16":
         net.actor, net.critic = pad_head(pad_first_layer(net.actor)), pad_first_layer(net.critic)
-    env = SplendorVecEnv(args.num_envs, seed=args.seed, shuffle="philox", autoreset=True, obs_format=args.obs_format)
+    env = SplendorVecEnv(args.num_envs, seed=args.seed, shuffle=args.shuffle, autoreset=True, obs_format=args.obs_format)
     env.reset()
     # rollout buffers in chunks so that 262,144 envs x 128 steps (40 GB of int32 observations) is not required at once
     chunk = max(1, min(args.num_steps, int(8e9 // (args.num_envs * 297 * env.obs.element_size()))))
