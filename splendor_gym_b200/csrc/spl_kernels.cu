@@ -1193,7 +1193,7 @@ static int g_ev_created = 0, g_ev_used = 0, g_timing = 0;
 
 extern "C" {
 
-int spl_version(void) { return 100; }
+int spl_version(void) { return 110; }  // 110: spl_envs.spare_slots, spl_step_io.flags, spl_refill_spares
 
 int spl_timing_enable(int on) {
 	if (on && !g_ev_created) {
