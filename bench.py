@@ -513,18 +513,47 @@ def run_b200(args):
                 np.copyto(h_act, info["next_action"].numpy())  # the host-side "policy": actions come back from host memory
             return f
 
+        # the node's ceiling for this path: streaming-store rate of the worker pool (uint8 -> int32 widening with
+        # non-temporal stores, the loop the path itself runs), measured in-process at the thread count actually used;
+        # with several ranks per node all ranks measure at the same time (they share the memory system)
+        host_threads = int(lib.spl_host_set_threads(0))
+        out_bytes = N * (1188 + 45 + 4 + 1 + 1 + 4)
+        if world > 1:
+            dist.barrier()
+        store_gbs = float(lib.spl_host_store_rate(max(1 << 20, out_bytes // host_threads), 5, 1))
+        fill_gbs = float(lib.spl_host_store_rate(max(1 << 20, out_bytes // host_threads), 5, 0))
+        if world > 1:
+            t = torch.tensor([store_gbs, fill_gbs], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            store_gbs, fill_gbs = float(t[0]), float(t[1])
+
         launches_e2e0 = lib.spl_launch_count()
         ems = time_host_loop(host_step(torch.int32), n_e2e)
         launches_e2e = (lib.spl_launch_count() - launches_e2e0) // (n_e2e + 5)
+        hs = env.host_stats()
+        share = hs["gpu_written_share"]
+        d2h = int(N * ((1.0 - share) * (148.5 + 17 + 16) + share * 1243) + 4 * ((N + 63) // 64))
+        written_gbs = out_bytes * world / (1e3 * ems / n_e2e) * 1e-3
         e2e = {"value": N * n_e2e * world / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N,
-               "d2h_bytes_per_step": N * (297 + 16), "lock_steps": n_e2e, "us_per_lock_step": 1e3 * ems / n_e2e,
-               "host_bytes_written_per_step": N * (1188 + 45 + 4 + 1 + 1 + 4), "host_threads": int(lib.spl_host_set_threads(0)),
+               "d2h_bytes_per_step": d2h, "lock_steps": n_e2e, "us_per_lock_step": 1e3 * ems / n_e2e,
+               "host_bytes_written_per_step": out_bytes, "host_threads": host_threads,
+               "host_written_gbs": written_gbs, "host_store_gbs": store_gbs, "host_fill_gbs": fill_gbs,
+               "frac_of_host_ceiling": written_gbs / store_gbs if store_gbs > 0 else None,
+               "host_ceiling": "spl_host_store_rate: the worker pool widening uint8 -> int32 with non-temporal stores into %d MB (mode 1; "
+                               "host_fill_gbs = plain streaming fill), best of 5, same threads and pinning as the path, summed over the "
+                               "ranks of the node measuring concurrently" % (out_bytes >> 20),
+               "gpu_written_share": share, "gpu_writable_results": bool(hs["gpu_writable"]),
+               "last_call_us": {k: hs[k] for k in ("call_us", "enqueued_us", "first_group_us", "workers_done_us", "gpu_share_done_us")},
                "kernels_per_lock_step": int(launches_e2e),
                "api": "SplendorVecEnv.step_host(actions) = C ABI spl_host_step: host int32 actions in; host int32 obs [N,297], int8 mask "
-                      "[N,45], float reward, bool terminated, info bits, next actions out. PCIe carries the compact form (297 B obs "
-                      "bytes + 16 B record per env); host threads widen chunk c while chunk c+1 is in flight"}
+                      "[N,45], float reward, bool terminated, info bits, next actions out. Step kernel (compact outputs in HBM) + push kernel: "
+                      "64-env groups are stored over PCIe into pinned host memory, nibble-packed (181.5 B per env) for the share that pinned "
+                      "host threads widen with non-temporal stores, already widened (1,243 B per env) for the gpu_written_share; the split "
+                      "follows the two finish times"}
         ums = time_host_loop(host_step(torch.uint8), n_e2e)
-        e2e_u8 = {"value": N * n_e2e * world / (ums * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": N * (297 + 16),
+        share8 = env.host_stats()["gpu_written_share"]
+        e2e_u8 = {"value": N * n_e2e * world / (ums * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * N,
+                  "d2h_bytes_per_step": int(N * ((1.0 - share8) * 181.5 + share8 * 352)), "gpu_written_share": share8,
                   "what": "same call with obs_dtype=uint8: the observation stays bytes on the host (same values; the policy casts to float anyway)"}
 
         # reference-typed arrays copied as they are (what round 1 first measured): PCIe-bound at 1,243 B per env-step

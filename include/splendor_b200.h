@@ -19,6 +19,7 @@
 #ifndef SPLENDOR_B200_H
 #define SPLENDOR_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -266,8 +267,24 @@ int spl_host_observe(spl_host_t *h, const spl_envs_t *envs, const spl_host_io_t 
  * (word 0 = mask bits 0-31; word 1 = mask bits 32-44 | reward code << 16 | terminated << 24; word 2 = info |
  * next action << 8) in HOST memory -> the non-NULL host arrays of `io`.  Pure CPU; needs no device. */
 int spl_host_expand(const uint8_t *obs_u8, const void *side, int64_t n, const spl_host_io_t *io);
-/* host threads used for widening (default: the cores this process may run on, at most 32); returns the count */
+/* host threads used for widening (n <= 0: query; default 3/4 of the cores this rank may run on, SPL_HOST_THREADS
+ * overrides); returns the count.  Workers are pinned to distinct cores unless spl_host_set_pinning(0). */
 int spl_host_set_threads(int n);
+int spl_host_set_pinning(int on);
+/* Result arrays the GPU can write directly (pinned + mapped, transparent huge pages requested).  When every non-NULL
+ * result pointer of spl_host_io_t lies in such memory (or in any cudaHostAlloc / cudaHostRegister'ed memory) and is
+ * 16-byte aligned, spl_host_step lets the GPU write a share of the envs ALREADY WIDENED over PCIe while host threads
+ * widen the rest; otherwise host threads widen everything.  Same values either way. */
+int spl_host_alloc(size_t bytes, void **out);
+int spl_host_free(void *ptr);
+/* timings of the last spl_host_step / spl_host_observe of `h` (microseconds from the start of the call):
+ * [0] whole call, [1] work enqueued, [2] last worker saw its first group, [3] slowest worker done, [4] GPU-written
+ * share landed, [5] share of the envs the GPU wrote widened, [6] worker threads, [7] 1 = result arrays GPU-writable */
+#define SPL_HOST_STATS 8
+int spl_host_get_stats(const spl_host_t *h, double *out);
+/* streaming-store rate of the worker pool in GB/s written (mode 0: fill, 1: uint8 -> int32 widening), the ceiling
+ * the host-buffer path is reported against (bench.py e2e.host_store_gbs).  Pure CPU; needs no device. */
+double spl_host_store_rate(int64_t bytes_per_thread, int reps, int mode);
 
 const char *spl_error_string(int code);
 int spl_version(void);

@@ -40,7 +40,7 @@ EXPORTS = (
     "spl_dual_combine", "spl_error_string", "spl_version", "spl_host_ret_table", "spl_launch_count",
     "spl_timing_enable", "spl_timing_read", "spl_rollout_random", "spl_scripted_action", "spl_masked_sample", "spl_gae",
     "spl_host_create", "spl_host_destroy", "spl_host_step", "spl_host_observe", "spl_host_set_threads", "spl_host_expand", "spl_rollout_plan", "spl_observe_policy", "spl_masked_sample_f16",
-    "spl_refill_spares",
+    "spl_refill_spares", "spl_host_set_pinning", "spl_host_alloc", "spl_host_free", "spl_host_get_stats", "spl_host_store_rate",
 )
 
 BOT_RANDOM, BOT_GREEDY_V1, BOT_BASIC_PRIORITY, BOT_GREEDY_V2 = 0, 1, 2, 3
@@ -152,6 +152,16 @@ def load():
     L.spl_host_expand.argtypes = [vp, vp, i64, C.POINTER(SplHostIO)]
     L.spl_host_set_threads.restype = C.c_int
     L.spl_host_set_threads.argtypes = [C.c_int]
+    L.spl_host_set_pinning.restype = C.c_int
+    L.spl_host_set_pinning.argtypes = [C.c_int]
+    L.spl_host_alloc.restype = C.c_int
+    L.spl_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.spl_host_free.restype = C.c_int
+    L.spl_host_free.argtypes = [vp]
+    L.spl_host_get_stats.restype = C.c_int
+    L.spl_host_get_stats.argtypes = [vp, C.POINTER(C.c_double)]
+    L.spl_host_store_rate.restype = C.c_double
+    L.spl_host_store_rate.argtypes = [i64, C.c_int, C.c_int]
     _lib = L
     return L
 

@@ -9,13 +9,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libsplendor_b200.so")
 SOURCES = ["spl_kernels.cu", "spl_policy.cu", "spl_host.cu", "spl_host_expand.cpp"]
-DEPS = ["spl_kernels.cu", "spl_policy.cu", "spl_host.cu", "spl_host_expand.cpp", "spl_core.cuh", "spl_tables_host.h", "../../include/splendor_b200.h", "../../include/spl_tables.h"]
+DEPS = ["spl_kernels.cu", "spl_policy.cu", "spl_host.cu", "spl_host_expand.cpp", "spl_core.cuh", "spl_tables_host.h", "spl_host_pool.h", "../../include/splendor_b200.h", "../../include/spl_tables.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--compiler-options", "-fPIC,-fopenmp",
-    "-shared", "-lgomp",
+    "--compiler-options", "-fPIC,-pthread",
+    "-shared", "-lpthread",
 ]
 
 

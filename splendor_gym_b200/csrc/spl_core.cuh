@@ -258,34 +258,49 @@ SPL_HD uint32_t spl_take3_combo(uint32_t a) { return (uint32_t)(SPL_TAKE3_COMBOS
 // ------------------------------------------------------------------------------------------------
 // legal_moves (engine/rules.py:40-93) as a 45-bit set for the player to move
 // ------------------------------------------------------------------------------------------------
-SPL_HD uint64_t spl_legal_mask(const SplState& s, const SplTables* T) {
-	uint32_t avail = spl_colours_ge(s.bank, 1);
-	uint32_t m_lo = T->take3_lut[avail];                 // bits 0..9   (:45-58)
-	m_lo |= spl_colours_ge(s.bank, 4) << 10;             // bits 10..14 (:61-63)
-	uint32_t wealth = spl_nib5_clamp7((s.tok[0] & 0xFFFFFFFFFFull) + s.bon[0]);
-	uint32_t gold = spl_byte(s.tok[0], 5);
-	// 12 board slots (:66-80) + my 3 reserved cards (:89-91): one loop body, kept rolled on purpose -- the step
-	// kernels are instruction-cache bound, not ALU bound
-	uint32_t afford = 0, present = 0;
-#pragma unroll 3
-	for (uint32_t slot = 0; slot < 15; slot++) {
-		uint32_t word = slot < 4 ? s.board[0] : (slot < 8 ? s.board[1] : (slot < 12 ? s.board[2] : s.res[0]));
-		uint32_t id = (word >> (8 * (slot & 3))) & 0xFFu;
+// The 15 card slots (12 board + my 3 reserved) are evaluated one at a time so that a caller can interleave them with
+// other work (the step kernels run them inside the observation-tile store loop, where the warp otherwise only waits
+// for the store queue); spl_legal_mask below is the plain sequence.
+struct SplMaskBuilder {
+	uint32_t wealth, gold, afford, present;
+	SPL_HD_MEMBER void begin(const SplState& s) {
+		wealth = spl_nib5_clamp7((s.tok[0] & 0xFFFFFFFFFFull) + s.bon[0]);
+		gold = spl_byte(s.tok[0], 5);
+		afford = 0, present = 0;
+	}
+	// board slots 0..11 (:66-80), my reserved cards 12..14 (:89-91)
+	SPL_HD_MEMBER void slot(const SplState& s, const SplTables* T, uint32_t k) {
+		uint32_t word = k < 4 ? s.board[0] : (k < 8 ? s.board[1] : (k < 12 ? s.board[2] : s.res[0]));
+		uint32_t id = (word >> (8 * (k & 3))) & 0xFFu;
 		uint32_t info = T->card_info[spl_min(id, 90u)];
 		bool here = id != SPL_EMPTY;
-		present |= here ? (1u << slot) : 0u;
-		afford |= (here && spl_shortfall(info, wealth) <= gold) ? (1u << slot) : 0u;
+		present |= here ? (1u << k) : 0u;
+		afford |= (here && spl_shortfall(info, wealth) <= gold) ? (1u << k) : 0u;
 	}
-	const uint32_t buy = afford & 0xFFFu, buyres = afford >> 12;
-	present &= 0xFFFu;
-	bool can_reserve = s.nres[0] < 3;                    // (:74, :83)
-	uint32_t blind = spl_compress_flags4(spl_ge_flags4(s.deckn, 1)) & 7u;
-	m_lo |= buy << 15;                                    // bits 15..26
-	uint32_t resv = can_reserve ? present : 0u;           // bits 27..38
-	uint32_t rb = can_reserve ? blind : 0u;               // bits 39..41
-	m_lo |= resv << 27;
-	uint32_t m_hi = (resv >> 5) | (rb << 7) | (buyres << 10);
-	return spl_u64(m_lo, m_hi);
+	SPL_HD_MEMBER uint64_t finish(const SplState& s, const SplTables* T) const {
+		uint32_t avail = spl_colours_ge(s.bank, 1);
+		uint32_t m_lo = T->take3_lut[avail];                 // bits 0..9   (:45-58)
+		m_lo |= spl_colours_ge(s.bank, 4) << 10;             // bits 10..14 (:61-63)
+		const uint32_t buy = afford & 0xFFFu, buyres = afford >> 12;
+		const uint32_t onboard = present & 0xFFFu;
+		bool can_reserve = s.nres[0] < 3;                    // (:74, :83)
+		uint32_t blind = spl_compress_flags4(spl_ge_flags4(s.deckn, 1)) & 7u;
+		m_lo |= buy << 15;                                    // bits 15..26
+		uint32_t resv = can_reserve ? onboard : 0u;           // bits 27..38
+		uint32_t rb = can_reserve ? blind : 0u;               // bits 39..41
+		m_lo |= resv << 27;
+		uint32_t m_hi = (resv >> 5) | (rb << 7) | (buyres << 10);
+		return spl_u64(m_lo, m_hi);
+	}
+};
+
+SPL_HD uint64_t spl_legal_mask(const SplState& s, const SplTables* T) {
+	SplMaskBuilder b;
+	b.begin(s);
+	// one loop body, kept rolled on purpose -- the step kernels are instruction-cache bound, not ALU bound
+#pragma unroll 3
+	for (uint32_t k = 0; k < 15; k++) b.slot(s, T, k);
+	return b.finish(s, T);
 }
 
 // legality of one action without building the whole mask (what `mask[action] != 1` checks,
@@ -441,7 +456,24 @@ SPL_HD bool spl_mt_deal_stream(uint32_t key, const uint32_t* G, uint8_t* deck, u
 
 // auto_return_tokens / _enforce_token_limit (engine/rules.py:150-193) for the mover (index 0).
 // `tp` = actual to_play, `turn` = turn_count, both BEFORE the end-of-turn increment (:160-165).
-SPL_HD void spl_enforce_token_limit(SplState& s, uint32_t tp, uint32_t turn, const uint64_t* ret_table, uint32_t& err) {
+// index of the tabulated token-return stream for (turn_count, to_play, hand total, bank total), or 0xFFFFFFFF outside
+// the domain that legal play reaches (turn 1..99, hand 11..13, bank 0..14)
+SPL_HD uint32_t spl_ret_index(uint32_t turn, uint32_t tp, uint32_t total, uint32_t bank_sum) {
+	const bool tabulated = (turn - 1u < 99u) && (total - 11u < 3u) && (bank_sum < 15u);
+	return tabulated ? (((turn - 1u) * 2u + tp) * 3u + (total - 11u)) * 15u + bank_sum : 0xFFFFFFFFu;
+}
+SPL_HD uint64_t spl_ret_load(const uint64_t* ret_table, uint32_t idx) {
+#if defined(__CUDA_ARCH__)
+	return __ldg(reinterpret_cast<const unsigned long long*>(ret_table) + idx);
+#else
+	return ret_table[idx];
+#endif
+}
+
+// `early_idx` / `early_val`: a table entry the caller loaded ahead of time (spl_env_step_t predicts the index from the
+// action); used when it is the entry needed, otherwise the entry is loaded here.
+SPL_HD void spl_enforce_token_limit(SplState& s, uint32_t tp, uint32_t turn, const uint64_t* ret_table, uint32_t& err,
+                                    uint32_t early_idx = 0xFFFFFFFFu, uint64_t early_val = 0) {
 	uint32_t total = spl_sum6(s.tok[0]);
 	if (total <= 10) return;
 	uint32_t remaining = total - 10;
@@ -450,16 +482,11 @@ SPL_HD void spl_enforce_token_limit(SplState& s, uint32_t tp, uint32_t turn, con
 	// anything else (hand-built states, or > 21 draws) is recomputed by spl_mt_top3_block -- one call site.
 	const uint64_t seed = ((uint64_t)turn * 1315423911ull) ^ ((uint64_t)tp * 2654435761ull) ^ ((uint64_t)total * 97531ull) ^
 	                      ((uint64_t)bank_sum * 31337ull);
-	const bool tabulated = (turn - 1u < 99u) && (total - 11u < 3u) && (bank_sum < 15u);
+	const uint32_t idx = spl_ret_index(turn, tp, total, bank_sum);
 	uint64_t stream = 0;
 	uint32_t pos = 21, next_blk = 0;
-	if (tabulated) {
-		uint32_t idx = (((turn - 1u) * 2u + tp) * 3u + (total - 11u)) * 15u + bank_sum;
-#if defined(__CUDA_ARCH__)
-		stream = __ldg(reinterpret_cast<const unsigned long long*>(ret_table) + idx);
-#else
-		stream = ret_table[idx];
-#endif
+	if (idx != 0xFFFFFFFFu) {
+		stream = idx == early_idx ? early_val : spl_ret_load(ret_table, idx);
 		pos = 0;
 		next_blk = 1;
 	}
@@ -494,28 +521,6 @@ SPL_HD void spl_enforce_token_limit(SplState& s, uint32_t tp, uint32_t turn, con
 		s.tok[0] -= (uint64_t)give << 40;
 		s.bank += (uint64_t)give << 40;
 	}
-}
-
-// The token-return stream (if this move overflows the hand) is indexed by sums that are only known after the
-// action, but in legitimate play bank + both hands = 25 tokens, so the three possible entries (hand 11/12/13) are
-// known from the opponent's hand at the START of the step: prefetch them into L1 so the dependent table load at the
-// end of the move does not wait on L2.  Purely a hint -- states that break the invariant just miss.
-SPL_HD void spl_prefetch_return_stream(const SplState& s, const uint64_t* ret_table) {
-#if defined(__CUDA_ARCH__) && !defined(SPL_NO_PREFETCH)
-	const uint32_t opp = spl_sum6(s.tok[1]);
-	const uint32_t turn = s.turn, tp = s.flags & SPL_FLAG_TO_PLAY;
-	if (turn - 1u < 99u && opp <= 10u && spl_sum6(s.tok[0]) >= 8u) {
-		const uint32_t base = ((turn - 1u) * 2u + tp) * 3u;
-#pragma unroll
-		for (uint32_t h = 0; h < 3; h++) {  // hand 11+h  =>  bank 25 - (11+h) - opp
-			const uint32_t idx = (base + h) * 15u + (14u - h - opp);
-			asm volatile("prefetch.global.L1 [%0];" ::"l"(ret_table + idx));
-		}
-	}
-#else
-	(void)s;
-	(void)ret_table;
-#endif
 }
 
 struct SplStepResult {
@@ -565,7 +570,6 @@ SPL_HD void spl_env_step_t(SplState& s, int32_t action, const uint8_t* deck, con
 		out.info = SPL_INFO_ERROR | SPL_INFO_TERMINATED;
 		return;
 	}
-	spl_prefetch_return_stream(s, ret_table);
 	const uint32_t avail = spl_colours_ge(s.bank, 1);
 	// any legal move? a non-empty bank always allows a take-3 (:45-58), so the full mask is only
 	// needed when all five colours are exhausted
@@ -624,6 +628,21 @@ SPL_HD void spl_env_step_t(SplState& s, int32_t action, const uint8_t* deck, con
 		pay_card = (s.res[0] >> (8 * remove_res)) & 0xFFu;
 	}
 	if (refill >= 0) pop_tier = refill >> 2;
+
+	// A token return (:150-193) reads ONE table entry, indexed by the hand and bank totals after the action.  Only take and
+	// reserve actions can push a hand over 10, and for them both totals are known right here: issue the load now, ~200
+	// instructions before spl_enforce_token_limit consumes it (which checks the index and reloads if a hand-built state
+	// broke the prediction).
+	uint32_t early_idx = 0xFFFFFFFFu;
+	uint64_t early_val = 0;
+	if (pay_card == SPL_EMPTY && remove_res < 0) {
+		const uint32_t ntake = reserve ? (spl_byte(s.bank, 5) > 0 ? 1u : 0u) : spl_sum6(take);
+		const uint32_t total = spl_sum6(s.tok[0]) + ntake;
+		if (total > 10) {
+			early_idx = spl_ret_index(s.turn, tp, total, spl_sum6(s.bank) - ntake);
+			if (early_idx != 0xFFFFFFFFu) early_val = spl_ret_load(ret_table, early_idx);
+		}
+	}
 
 	// deck.pop() from the END of the list (:127, :244)
 	uint32_t popped = SPL_EMPTY;
@@ -702,7 +721,7 @@ SPL_HD void spl_env_step_t(SplState& s, int32_t action, const uint8_t* deck, con
 	}
 
 	uint32_t err = 0;
-	spl_enforce_token_limit(s, tp, s.turn, ret_table, err);  // (:261)
+	spl_enforce_token_limit(s, tp, s.turn, ret_table, err, early_idx, early_val);  // (:261)
 
 	// end of turn (:263-285)
 	uint32_t flags = s.flags;
@@ -882,6 +901,37 @@ SPL_HD void spl_export_row(const SplState& s, const uint8_t* deck, int32_t* row)
 		int dn = (int)((s.deckn >> (8 * t)) & 0xFFu);
 		for (int k = 0; k < dn; k++) row[off[t] + k] = (int32_t)deck[doff[t] + k];
 	}
+}
+
+// Is a flat row inside the domain of the packed state?  Counters are bytes whose SWAR arithmetic needs values < 128,
+// ids index the 90-card / 10-noble tables, list lengths are at most 3.  spl_import_state rejects rows that are not
+// (nothing is truncated silently).
+SPL_HD bool spl_row_valid(const int32_t* row) {
+	bool ok = true;
+	for (int i = 0; i < 6; i++) ok = ok && (uint32_t)row[i] < 128u;
+	for (int p = 0; p < 2; p++) {
+		const int o = SPL_ROW_PLAYER0 + SPL_ROW_PLAYER_STRIDE * p;
+		for (int i = 0; i < 12; i++) ok = ok && (uint32_t)row[o + i] < 128u;  // tokens, bonuses, prestige
+		const int32_t nres = row[o + 12], nnob = row[o + 19];
+		ok = ok && nres >= 0 && nres <= 3 && nnob >= 0 && nnob <= 3;
+		for (int i = 0; i < 3; i++) {
+			if (i < nres) ok = ok && (uint32_t)row[o + 13 + i] < 90u;
+			if (i < nnob) ok = ok && (uint32_t)row[o + 20 + i] < 10u;
+		}
+	}
+	for (int k = 0; k < 12; k++) ok = ok && row[SPL_ROW_BOARD + k] >= -1 && row[SPL_ROW_BOARD + k] < 90;
+	const int off[3] = {SPL_ROW_DECK1, SPL_ROW_DECK2, SPL_ROW_DECK3};
+	const int dlen[3] = {40, 30, 20};
+	for (int t = 0; t < 3; t++) {
+		const int32_t dn = row[SPL_ROW_DECK_SIZES + t];
+		ok = ok && dn >= 0 && dn <= dlen[t];
+		for (int k = 0; k < dlen[t]; k++)
+			if (k < dn) ok = ok && (uint32_t)row[off[t] + k] < 90u;
+	}
+	for (int i = 0; i < 3; i++) ok = ok && row[SPL_ROW_NOBLES + i] >= -1 && row[SPL_ROW_NOBLES + i] < 10;
+	ok = ok && (uint32_t)row[SPL_ROW_TO_PLAY] < 2u && (uint32_t)row[SPL_ROW_TURN_COUNT] < 256u && (uint32_t)row[SPL_ROW_MOVE_COUNT] < 256u;
+	ok = ok && row[SPL_ROW_WINNER] >= -1 && row[SPL_ROW_WINNER] < 2;
+	return ok;
 }
 
 SPL_HD void spl_import_row(const int32_t* row, SplState& s, uint8_t* deck) {

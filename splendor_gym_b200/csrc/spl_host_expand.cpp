@@ -3,21 +3,26 @@
 // (envs/splendor_env.py:51-90: int32 observation, int8 action mask, float reward, bool terminated).
 // Pure format conversion, no game logic: every value was computed by the CUDA step kernel.
 //
-// The work is memory-bound (1,243 B written per env-step), so: OpenMP over blocks of envs, AVX2 zero-extension
-// with non-temporal stores for the observation (no read-for-ownership of the destination lines), a 256-entry
-// bits->bytes table for the mask.
+// The work is memory-bound (1,243 B written per env-step), so: a pool of pinned worker threads that own contiguous
+// ranges of envs, AVX-512 / AVX2 zero-extension with non-temporal stores for the observation (no read-for-ownership
+// of the destination lines), a 256-entry bits->bytes table for the mask.  Workers find their input by polling arrival
+// flags the GPU writes into pinned host memory behind each 64-env group (spl_host.cu, spl_push_kernel).
+#include <pthread.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
-#include <omp.h>
+#include <atomic>
+
 #include <sched.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
 
 #include "../../include/splendor_b200.h"
+#include "spl_host_pool.h"
 
 namespace {
 
@@ -77,6 +82,16 @@ __attribute__((target("avx512f"))) void widen_avx512(const uint8_t* src, int32_t
 	for (; i < n; i++) dst[i] = (int32_t)src[i];
 	_mm_sfence();
 }
+__attribute__((target("avx512f"))) void fill_avx512(void* dst, size_t bytes) {
+	const __m512i v = _mm512_set1_epi32(1);
+	char* p = (char*)dst;
+	for (size_t i = 0; i + 64 <= bytes; i += 64) _mm512_stream_si512((__m512i*)(p + i), v);
+	_mm_sfence();
+}
+__attribute__((target("avx2"))) void stream_lines(void* dst, const void* src, size_t bytes) {
+	for (size_t i = 0; i < bytes; i += 32) _mm256_stream_si256((__m256i*)((char*)dst + i), _mm256_loadu_si256((const __m256i*)((const char*)src + i)));
+	_mm_sfence();
+}
 int simd_level() {  // 0 scalar, 2 AVX2, 5 AVX-512 (SPL_HOST_SIMD overrides downwards)
 	static const int v = [] {
 		int lvl = __builtin_cpu_supports("avx512f") ? 5 : (__builtin_cpu_supports("avx2") ? 2 : 0);
@@ -96,100 +111,364 @@ inline void widen(const uint8_t* src, int32_t* dst, size_t n) {
 	widen_scalar(src, dst, n);
 }
 
-int g_threads = 0;
+inline void cpu_relax() {
+#if defined(__x86_64__)
+	_mm_pause();
+#endif
+}
 
 }  // namespace
 
-// widen envs [lo, hi): obs_u8 / side are the staging arrays (indexed by env), outputs are the caller's arrays
-static void expand_block(const uint8_t* obs_u8, const uint32_t* side, int64_t lo, int64_t hi, const spl_host_io_t* io) {
-	if (io->obs) widen(obs_u8 + lo * 297, io->obs + lo * 297, (size_t)(hi - lo) * 297);
-	if (io->obs_u8 && io->obs_u8 != obs_u8) memcpy(io->obs_u8 + lo * 297, obs_u8 + lo * 297, (size_t)(hi - lo) * 297);
-	for (int64_t i = lo; i < hi; i++) {
-		const uint32_t x = side[4 * i], y = side[4 * i + 1], z = side[4 * i + 2];
-		if (io->mask) {
-			const uint64_t m = (uint64_t)x | ((uint64_t)(y & 0x1FFFu) << 32);
-			int8_t* row = io->mask + i * 45;
-			uint64_t w;
-			for (int q = 0; q < 5; q++) {
-				w = kBits.v[(m >> (8 * q)) & 0xFF];
-				memcpy(row + 8 * q, &w, 8);
-			}
-			w = kBits.v[(m >> 40) & 0x1F];
-			memcpy(row + 40, &w, 5);
-		}
-		if (io->reward) io->reward[i] = kRewardOfCode[(y >> 16) & 7];
-		if (io->terminated) io->terminated[i] = (uint8_t)((y >> 24) & 1);
-		if (io->info) io->info[i] = (uint8_t)(z & 0xFF);
-		if (io->next_action) io->next_action[i] = (int32_t)((z >> 8) & 0xFF);
-	}
+double spl_now_us() {
+	timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec * 1e6 + (double)ts.tv_nsec * 1e-3;
 }
 
-// All chunks of one lock-step in ONE parallel region (a fork/join per chunk costs more than widening a chunk):
-// thread 0 waits for chunk c's copy (`wait(ctx, c)`, a cudaEventSynchronize) and publishes it; the others spin on the
-// counter; then every thread widens its share of the chunk.  bounds[c]..bounds[c+1] = envs of chunk c.
-void spl_expand_chunks(const uint8_t* obs_u8, const uint32_t* side, const int64_t* bounds, int chunks, const spl_host_io_t* io,
-                       int (*wait)(void*, int), void* ctx, int* rc_out) {
-	const int64_t blk = 64;  // envs per task: 19 KB of observation bytes in, 76 KB out
-	const int nthreads = g_threads > 0 ? g_threads : omp_get_max_threads();
-	int ready = 0, rc = 0;
-#pragma omp parallel num_threads(nthreads)
-	{
-		const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
-		for (int c = 0; c < chunks; c++) {
-			if (tid == 0) {
-				int r = wait ? wait(ctx, c) : 0;
-				if (r) __atomic_store_n(&rc, r, __ATOMIC_RELAXED);
-				__atomic_store_n(&ready, c + 1, __ATOMIC_RELEASE);
-			} else {
-				for (unsigned spins = 0; __atomic_load_n(&ready, __ATOMIC_ACQUIRE) <= c; spins++) {
+// whole cache lines to a 64-byte aligned destination without reading them first; anything else through memcpy
+static void stream_copy(void* dst, const void* src, size_t bytes) {
 #if defined(__x86_64__)
-					_mm_pause();
-#endif
-					if ((spins & 1023u) == 1023u) sched_yield();  // oversubscribed hosts: let thread 0 run
-				}
-			}
-			if (__atomic_load_n(&rc, __ATOMIC_RELAXED)) continue;
-			const int64_t b = bounds[c], e = bounds[c + 1];
-			const int64_t nblk = (e - b + blk - 1) / blk;
-			// contiguous share per thread (streams well); thread 0 (which also waits on the device) gets the tail
-			const int64_t per = (nblk + nt - 1) / nt;
-			const int64_t k0 = per * ((tid + nt - 1) % nt), k1 = k0 + per < nblk ? k0 + per : nblk;
-			for (int64_t k = k0; k < k1; k++) {
-				const int64_t lo = b + k * blk, hi = lo + blk < e ? lo + blk : e;
-				expand_block(obs_u8, side, lo, hi, io);
-			}
-		}
-	}
-	if (rc_out) *rc_out = rc;
-}
-
-void spl_expand_range(const uint8_t* obs_u8, const uint32_t* side, int64_t b, int64_t e, const spl_host_io_t* io) {
-	const int64_t bounds[2] = {b, e};
-	spl_expand_chunks(obs_u8, side, bounds, 1, io, nullptr, nullptr, nullptr);
-}
-
-void spl_parallel_copy(void* dst, const void* src, size_t bytes) {
-	const size_t blk = 1 << 16;
-	const int64_t nblk = (int64_t)((bytes + blk - 1) / blk);
-	const int nthreads = g_threads > 0 ? g_threads : omp_get_max_threads();
-	if (nblk <= 4) {
-		memcpy(dst, src, bytes);
+	if ((((uintptr_t)dst | bytes) & 63) == 0 && simd_level() >= 2) {
+		stream_lines(dst, src, bytes);
 		return;
 	}
-#pragma omp parallel for schedule(static) num_threads(nthreads)
-	for (int64_t k = 0; k < nblk; k++) {
-		const size_t o = (size_t)k * blk;
-		memcpy((char*)dst + o, (const char*)src + o, o + blk <= bytes ? blk : bytes - o);
+#endif
+	memcpy(dst, src, bytes);
+}
+
+// widen envs [lo, hi), hi - lo <= SPL_HOST_GROUP: obs_u8 / side are the staging arrays (indexed by env), outputs are
+// the caller's arrays.  The small outputs of a group are assembled in L1 and leave as whole cache lines too (a full
+// group is 2,880 B of mask, 256 B of rewards, ...: no read-for-ownership of the destination when it is 64-byte aligned).
+void spl_expand_block(const uint8_t* obs_u8, const uint32_t* side, int64_t lo, int64_t hi, const spl_host_io_t* io) {
+	if (io->obs) widen(obs_u8 + lo * 297, io->obs + lo * 297, (size_t)(hi - lo) * 297);
+	if (io->obs_u8 && io->obs_u8 != obs_u8) stream_copy(io->obs_u8 + lo * 297, obs_u8 + lo * 297, (size_t)(hi - lo) * 297);
+	alignas(64) int8_t mask[SPL_HOST_GROUP * 45 + 8];
+	alignas(64) float reward[SPL_HOST_GROUP];
+	alignas(64) uint8_t term[SPL_HOST_GROUP], info[SPL_HOST_GROUP];
+	alignas(64) int32_t next[SPL_HOST_GROUP];
+	const int m = (int)(hi - lo);
+	for (int i = 0; i < m; i++) {
+		const uint32_t* rec = side + 4 * (lo + i);
+		const uint32_t x = rec[0], y = rec[1], z = rec[2];
+		if (io->mask) {
+			const uint64_t mk = (uint64_t)x | ((uint64_t)(y & 0x1FFFu) << 32);
+			int8_t* row = mask + i * 45;
+			for (int q = 0; q < 6; q++) {  // the last 8-byte store spills 3 bytes into the next row, which is written after it
+				const uint64_t w = kBits.v[(mk >> (8 * q)) & 0xFF];
+				memcpy(row + 8 * q, &w, 8);
+			}
+		}
+		reward[i] = kRewardOfCode[(y >> 16) & 7];
+		term[i] = (uint8_t)((y >> 24) & 1);
+		info[i] = (uint8_t)(z & 0xFF);
+		next[i] = (int32_t)((z >> 8) & 0xFF);
+	}
+	if (io->mask) stream_copy(io->mask + lo * 45, mask, (size_t)m * 45);
+	if (io->reward) stream_copy(io->reward + lo, reward, (size_t)m * 4);
+	if (io->terminated) stream_copy(io->terminated + lo, term, (size_t)m);
+	if (io->info) stream_copy(io->info + lo, info, (size_t)m);
+	if (io->next_action) stream_copy(io->next_action + lo, next, (size_t)m * 4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Worker pool.  One job = one lock-step: worker j owns the contiguous groups [start_j, start_j + len_j) of the
+// CPU share and widens group g as soon as flags[g] == seq.  Workers spin between jobs for a while (a vector loop
+// calls spl_host_step back to back), then sleep on a condition variable.
+// ------------------------------------------------------------------------------------------------
+struct SplPool {
+	int threads = 0;  // including the caller (worker 0)
+	pthread_t tid[SPL_POOL_MAX];
+	int index[SPL_POOL_MAX];
+	std::atomic<uint64_t> generation{0};
+	std::atomic<int> done{0};
+	std::atomic<int> stop{0};
+	std::atomic<int> sleepers{0};
+	pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+	pthread_cond_t cv = PTHREAD_COND_INITIALIZER;
+	SplHostJob job;
+	int cpus[SPL_POOL_MAX];  // core of worker j (-1: not pinned)
+};
+
+static SplPool* g_pool = nullptr;
+static int g_threads = 0;
+static int g_pin = 1;
+
+void spl_job_share(const SplHostJob* job, int j, int64_t* start, int64_t* len) {
+	const int64_t base = job->cpu_groups / job->threads, rem = job->cpu_groups % job->threads;
+	*start = (int64_t)j * base + (j < rem ? j : rem);
+	*len = base + (j < rem ? 1 : 0);
+}
+
+// nibble-packed group (spl_push_kernel) -> observation bytes: entries 2i / 2i+1 are the low / high nibble of byte i,
+// the 17 columns that can exceed 15 follow as whole bytes per env
+static const int kWideCols[17] = {12, 13, 14, 15, 16, 17, 25, 26, 27, 28, 29, 30, 290, 291, 292, 293, 295};
+static void unpack_group(const uint8_t* src, int m, uint8_t* out) {
+	const int nbytes = m * 297;
+	const int nn = (nbytes + 1) / 2;
+	int i = 0;
+#if defined(__x86_64__)
+	const __m128i lowmask = _mm_set1_epi8(0x0F);
+	for (; i + 16 <= nn; i += 16) {
+		const __m128i v = _mm_loadu_si128((const __m128i*)(src + i));
+		const __m128i lo = _mm_and_si128(v, lowmask), hi = _mm_and_si128(_mm_srli_epi16(v, 4), lowmask);
+		_mm_storeu_si128((__m128i*)(out + 2 * i), _mm_unpacklo_epi8(lo, hi));
+		_mm_storeu_si128((__m128i*)(out + 2 * i + 16), _mm_unpackhi_epi8(lo, hi));
+	}
+#endif
+	for (; i < nn; i++) out[2 * i] = src[i] & 15, out[2 * i + 1] = src[i] >> 4;
+	const uint8_t* wide = src + SPL_HOST_GROUP * 297 / 2;
+	for (int e = 0; e < m; e++)
+		for (int w = 0; w < 17; w++) out[e * 297 + kWideCols[w]] = wide[e * 17 + w];
+}
+
+static void run_share(SplHostJob* job, int j) {
+	int64_t start, len;
+	spl_job_share(job, j, &start, &len);
+	const int64_t G = SPL_HOST_GROUP;
+	double t_first = 0;
+	alignas(64) uint8_t tmp[SPL_HOST_GROUP * 297 + 64];
+	const bool want_obs = job->io.obs || job->io.obs_u8;
+	for (int64_t r = 0; r < len; r++) {
+		const int64_t g = start + r;
+		uint32_t f = job->seq;
+		if (job->flags) {
+			unsigned spins = 0;
+			while (((f = __atomic_load_n(job->flags + g, __ATOMIC_ACQUIRE)) & 0x7FFFFFFFu) != job->seq) {
+				if (job->abort.load(std::memory_order_relaxed)) return;
+				// worker 0 is the thread that owns the CUDA context: it watches the stream for errors while it waits
+				if (j == 0 && job->poll && (++spins & 0x3FFFu) == 0 && job->poll(job->poll_ctx)) {
+					job->abort.store(1);
+					return;
+				}
+				cpu_relax();
+			}
+		}
+		if (r == 0) t_first = spl_now_us();
+		const int64_t lo = g * G, hi = lo + G < job->n ? lo + G : job->n;
+		if (job->packed && want_obs && !(f >> 31)) {
+			unpack_group(job->obs_u8 + lo * 297, (int)(hi - lo), tmp);
+			spl_expand_block(tmp - lo * 297, job->side, lo, hi, &job->io);
+		} else {
+			spl_expand_block(job->obs_u8, job->side, lo, hi, &job->io);
+		}
+	}
+	job->t_first[j] = t_first;
+	job->t_done[j] = spl_now_us();
+}
+
+static void* worker_main(void* arg) {
+	SplPool* P = g_pool;
+	const int j = *(int*)arg;
+	if (P->cpus[j] >= 0) {
+		cpu_set_t set;
+		CPU_ZERO(&set);
+		CPU_SET(P->cpus[j], &set);
+		pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+	}
+	uint64_t seen = 0;
+	for (;;) {
+		// wait for the next generation: spin ~0.3 ms, then sleep
+		unsigned spins = 0;
+		while (P->generation.load(std::memory_order_acquire) == seen && !P->stop.load(std::memory_order_relaxed)) {
+			cpu_relax();
+			if (++spins > 200000u) {
+				pthread_mutex_lock(&P->mu);
+				P->sleepers.fetch_add(1);
+				while (P->generation.load(std::memory_order_acquire) == seen && !P->stop.load()) pthread_cond_wait(&P->cv, &P->mu);
+				P->sleepers.fetch_sub(1);
+				pthread_mutex_unlock(&P->mu);
+				spins = 0;
+			}
+		}
+		if (P->stop.load()) return nullptr;
+		seen = P->generation.load(std::memory_order_acquire);
+		if (P->job.custom) P->job.custom(P->job.custom_ctx, j);
+		else if (j < P->job.threads) run_share(&P->job, j);
+		P->done.fetch_add(1, std::memory_order_release);
 	}
 }
+
+static void pool_shutdown() {
+	SplPool* P = g_pool;
+	if (!P) return;
+	P->stop.store(1);
+	pthread_mutex_lock(&P->mu);
+	pthread_cond_broadcast(&P->cv);
+	pthread_mutex_unlock(&P->mu);
+	for (int j = 1; j < P->threads; j++) pthread_join(P->tid[j], nullptr);
+	delete P;
+	g_pool = nullptr;
+}
+
+// the cores this process may use, rotated so that the ranks of a node (LOCAL_RANK / LOCAL_WORLD_SIZE) take disjoint sets
+static void choose_cpus(SplPool* P) {
+	for (int j = 0; j < SPL_POOL_MAX; j++) P->cpus[j] = -1;
+	if (!g_pin) return;
+	cpu_set_t set;
+	if (sched_getaffinity(0, sizeof(set), &set) != 0) return;
+	int avail[1024], na = 0;
+	for (int c = 0; c < CPU_SETSIZE && na < 1024; c++)
+		if (CPU_ISSET(c, &set)) avail[na++] = c;
+	if (na == 0) return;
+	const char* lr = getenv("LOCAL_RANK");
+	const char* lws = getenv("LOCAL_WORLD_SIZE");
+	const int rank = lr ? atoi(lr) : 0, ws = lws && atoi(lws) > 0 ? atoi(lws) : 1;
+	const int per = na / ws > 0 ? na / ws : 1;
+	const int first = (rank % ws) * per;
+	// worker 0 is the caller's thread and is left where the OS put it; workers 1.. take the rank's cores from the top
+	for (int j = 1; j < P->threads; j++) P->cpus[j] = avail[(first + per - 1 - ((j - 1) % per)) % na];
+}
+
+// default size of the pool: 3/4 of the cores this rank may use.  Measured (16 vCPUs, tools/microbench/host_bw.c):
+// streaming stores peak at 8-12 threads (200 GB/s) and drop to 150 GB/s at 16.
+static void default_threads() {
+	cpu_set_t set;
+	int n = 0;
+	if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+	if (n < 1) n = 1;
+	const char* lws = getenv("LOCAL_WORLD_SIZE");  // one process per GPU (torchrun): the ranks of a node share its cores
+	if (lws && atoi(lws) > 1) n /= atoi(lws);
+	n = (n * 3 + 3) / 4;
+	const char* e = getenv("SPL_HOST_THREADS");
+	if (e && atoi(e) > 0) n = atoi(e);
+	if (n < 1) n = 1;
+	if (n > 32) n = 32;
+	g_threads = n;
+	const char* pin = getenv("SPL_HOST_PIN");
+	if (pin && atoi(pin) == 0) g_pin = 0;
+}
+
+static SplPool* pool_get() {
+	if (g_threads <= 0) default_threads();
+	const int want = g_threads > 0 ? g_threads : 1;
+	if (g_pool && g_pool->threads == want) return g_pool;
+	pool_shutdown();
+	SplPool* P = new SplPool();
+	P->threads = want > SPL_POOL_MAX ? SPL_POOL_MAX : want;
+	choose_cpus(P);
+	g_pool = P;
+	for (int j = 1; j < P->threads; j++) {
+		P->index[j] = j;
+		pthread_create(&P->tid[j], nullptr, worker_main, &P->index[j]);
+	}
+	static bool registered = false;
+	if (!registered) {
+		registered = true;
+		atexit(pool_shutdown);
+	}
+	return P;
+}
+
+SplHostJob* spl_pool_job() { return &pool_get()->job; }
+int spl_pool_threads() { return pool_get()->threads; }
+
+// run the job that was filled into spl_pool_job(): the caller works as worker 0 and returns when every share is done
+void spl_pool_run() {
+	SplPool* P = pool_get();
+	SplHostJob* job = &P->job;
+	if (job->threads > P->threads) job->threads = P->threads;
+	if (job->threads < 1) job->threads = 1;
+	job->abort.store(0);
+	P->done.store(0, std::memory_order_relaxed);
+	P->generation.fetch_add(1, std::memory_order_release);
+	if (P->sleepers.load() > 0) {
+		pthread_mutex_lock(&P->mu);
+		pthread_cond_broadcast(&P->cv);
+		pthread_mutex_unlock(&P->mu);
+	}
+	run_share(job, 0);
+	if (job->after_share0) job->after_share0(job);
+	while (P->done.load(std::memory_order_acquire) < P->threads - 1) cpu_relax();
+}
+
+// streaming-store rate of the pool (GB/s written) over `bytes` per thread, `reps` passes: the ceiling the widened
+// results are reported against (bench.py e2e.host_store_gbs).  mode 0: fill, 1: widen u8 -> int32 from a 1/4-size source
+extern "C" double spl_host_store_rate(int64_t bytes_per_thread, int reps, int mode) {
+	SplPool* P = pool_get();
+	const int T = P->threads;
+	if (bytes_per_thread < 4096) bytes_per_thread = 4096;
+	bytes_per_thread &= ~(int64_t)4095;
+	char* dst = nullptr;
+	uint8_t* src = nullptr;
+	if (posix_memalign((void**)&dst, 4096, (size_t)bytes_per_thread * T)) return 0.0;
+	if (posix_memalign((void**)&src, 4096, (size_t)bytes_per_thread / 4 * T)) {
+		free(dst);
+		return 0.0;
+	}
+	memset(dst, 0, (size_t)bytes_per_thread * T);
+	memset(src, 3, (size_t)bytes_per_thread / 4 * T);
+	struct Ctx {
+		char* dst;
+		uint8_t* src;
+		int64_t bytes;
+		int mode;
+	} ctx{dst, src, bytes_per_thread, mode};
+	// a job whose "groups" are whole per-thread buffers: reuse the pool through a custom block function
+	double best = 0.0;
+	for (int r = 0; r < reps + 1; r++) {
+		SplHostJob* job = &P->job;
+		*job = SplHostJob();
+		job->threads = T;
+		job->custom = [](void* c, int j) {
+			Ctx* x = (Ctx*)c;
+#if defined(__x86_64__)
+			if (x->mode == 0 && simd_level() >= 5) {
+				fill_avx512(x->dst + (size_t)j * x->bytes, (size_t)x->bytes);
+				return;
+			}
+#endif
+			if (x->mode == 0) memset(x->dst + (size_t)j * x->bytes, 1, (size_t)x->bytes);
+			else widen(x->src + (size_t)j * (x->bytes / 4), (int32_t*)(x->dst + (size_t)j * x->bytes), (size_t)x->bytes / 4);
+		};
+		job->custom_ctx = &ctx;
+		const double t0 = spl_now_us();
+		spl_pool_run_custom();
+		const double dt = spl_now_us() - t0;
+		const double gbs = (double)bytes_per_thread * T / dt * 1e-3;
+		if (r > 0 && gbs > best) best = gbs;
+	}
+	free(dst);
+	free(src);
+	return best;
+}
+
+void spl_pool_run_custom() {
+	SplPool* P = pool_get();
+	SplHostJob* job = &P->job;
+	// custom jobs run through the same generation hand-shake; run_share is bypassed by cpu_groups == 0
+	job->cpu_groups = 0;
+	job->abort.store(0);
+	P->done.store(0, std::memory_order_relaxed);
+	P->generation.fetch_add(1, std::memory_order_release);
+	if (P->sleepers.load() > 0) {
+		pthread_mutex_lock(&P->mu);
+		pthread_cond_broadcast(&P->cv);
+		pthread_mutex_unlock(&P->mu);
+	}
+	job->custom(job->custom_ctx, 0);
+	while (P->done.load(std::memory_order_acquire) < P->threads - 1) cpu_relax();
+}
+
+void spl_parallel_copy(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 
 extern "C" int spl_host_expand(const uint8_t* obs_u8, const void* side, int64_t n, const spl_host_io_t* io) {
 	if (!side || !io || n <= 0 || ((io->obs || io->obs_u8) && !obs_u8)) return SPL_E_BADARG;
-	spl_expand_range(obs_u8, (const uint32_t*)side, 0, n, io);
+	SplHostJob* job = spl_pool_job();
+	*job = SplHostJob();
+	job->obs_u8 = obs_u8, job->side = (const uint32_t*)side, job->io = *io, job->n = n;
+	job->threads = spl_pool_threads();
+	job->cpu_groups = (n + SPL_HOST_GROUP - 1) / SPL_HOST_GROUP;
+	spl_pool_run();
 	return 0;
 }
 
 extern "C" int spl_host_set_threads(int n) {
-	if (n > 0) g_threads = n;
-	return g_threads > 0 ? g_threads : omp_get_max_threads();
+	if (n > 0) g_threads = n > SPL_POOL_MAX ? SPL_POOL_MAX : n;
+	else if (g_threads <= 0) default_threads();
+	return g_threads;
+}
+
+extern "C" int spl_host_set_pinning(int on) {
+	g_pin = on ? 1 : 0;
+	return g_pin;
 }

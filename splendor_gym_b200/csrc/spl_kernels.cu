@@ -578,7 +578,10 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 			__syncwarp();
 			if (valid)
 				__stcs(p.side + env, make_uint4((uint32_t)m, (uint32_t)(m >> 32) | (spl_reward_code(r.reward) << 16) | ((uint32_t)r.terminated << 24),
-				                               (uint32_t)r.info | ((uint32_t)sampled << 8), 0u));
+				                               (uint32_t)r.info | ((uint32_t)sampled << 8),
+				                               // bit 0: a token count >= 16 (hand-built states only): this env's observation does not fit
+				                               // the nibble-packed transfer form of spl_push_kernel
+				                               ((s.bank | s.tok[0] | s.tok[1]) & 0xF0F0F0F0F0F0ull) != 0 ? 1u : 0u));
 		} else {
 			spl_tile_emit(p, tl, s, w, env, valid, OUT == SPL_OUT_F16 ? nullptr : p.obs, p.mask, p.next_action, t, m);
 			if (OUT == SPL_OUT_F16) {
@@ -1221,6 +1224,7 @@ int spl_timing_read(double* total_ms, int64_t* count) {
 }
 
 int64_t spl_launch_count(void) { return g_launches; }
+
 
 #ifdef SPL_DEBUG_SM_UNITS
 int spl_debug_sm_units(unsigned int* out, int reset) {

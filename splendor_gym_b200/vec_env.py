@@ -131,6 +131,8 @@ class SplendorVecEnv:
             scratch=self.scratch.data_ptr(), stride=n, n=n, env_offset=int(env_offset), seed_base=int(seed),
             shuffle_mode=self.shuffle_mode, spare_slots=self.spare_slots, spare=None if self.spare is None else self.spare.data_ptr(),
         )
+        self._envs_ref = C.byref(self._envs)
+        self._device_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         # gymnasium.vector-style attributes (what gym.vector.SyncVectorEnv exposes, ppo_splendor.py:151-159)
         from .envs._gym_compat import spaces
         import numpy as _np
@@ -309,73 +311,133 @@ class SplendorVecEnv:
             handle = C.c_void_p()
             with torch.cuda.device(self.device):
                 L.check(self.lib.spl_host_create(n, 0, C.byref(handle)), "spl_host_create")
-            H = dict(handle=handle, io=L.SplHostIO(),
-                     mask=torch.zeros((n, L.NUM_ACTIONS), dtype=torch.int8), reward=torch.zeros(n, dtype=torch.float32),
-                     terminated=torch.zeros(n, dtype=torch.uint8), info_bits=torch.zeros(n, dtype=torch.uint8),
-                     next_action=torch.zeros(n, dtype=torch.int32), truncated=torch.zeros(n, dtype=torch.bool))
+            H = dict(handle=handle, blocks=[], obs_by_dtype={}, plans={})
             self._host = H
-        H["obs"] = torch.zeros((n, L.OBS_DIM), dtype=obs_dtype)
-        if obs_dtype == torch.uint8:
-            H["obs"] = H["obs"].pin_memory()  # the copy engine writes the bytes straight into it
+            for name, shape, dt in (("mask", (n, L.NUM_ACTIONS), torch.int8), ("reward", (n,), torch.float32),
+                                    ("terminated", (n,), torch.uint8), ("info_bits", (n,), torch.uint8),
+                                    ("next_action", (n,), torch.int32)):
+                H[name] = self._host_array(H, shape, dt)
+            H["truncated"] = torch.zeros(n, dtype=torch.bool)
+        if obs_dtype not in H["obs_by_dtype"]:
+            H["obs_by_dtype"][obs_dtype] = self._host_array(H, (n, L.OBS_DIM), obs_dtype)
+        H["obs"] = H["obs_by_dtype"][obs_dtype]
         return H
 
-    def _host_call(self, fn, name, actions, obs_dtype, sample_next, autoreset):
-        H = self._host_setup(obs_dtype)
-        io = H["io"]
-        io.actions = actions
-        io.obs = H["obs"].data_ptr() if obs_dtype == torch.int32 else None
-        io.obs_u8 = H["obs"].data_ptr() if obs_dtype == torch.uint8 else None
-        io.mask, io.reward = H["mask"].data_ptr(), H["reward"].data_ptr()
-        io.terminated, io.info = H["terminated"].data_ptr(), H["info_bits"].data_ptr()
-        io.next_action = H["next_action"].data_ptr() if sample_next else None
-        io.stats = self.stats.data_ptr()
-        io.action_key = self.action_key
-        io.autoreset = int(autoreset)
+    def _host_array(self, H, shape, dtype) -> torch.Tensor:
+        """A zeroed CPU tensor over ``spl_host_alloc`` memory (pinned + mapped, huge pages requested): the GPU can write
+        a share of the results into it directly.  Plain host memory to the caller (``.numpy()`` works)."""
+        import numpy as np
+
+        count = 1
+        for d in shape:
+            count *= int(d)
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        ptr = C.c_void_p()
         with torch.cuda.device(self.device):
-            L.check(fn(H["handle"], C.byref(self._envs), C.byref(io), self._stream()), name)
-        return H
+            L.check(self.lib.spl_host_alloc(max(nbytes, 1), C.byref(ptr)), "spl_host_alloc")
+        H["blocks"].append(ptr)
+        buf = (C.c_uint8 * nbytes).from_address(ptr.value)
+        return torch.from_numpy(np.frombuffer(buf, dtype=np.uint8)).view(dtype).view(*shape)
+
+    def _host_plan(self, obs_dtype, sample_next):
+        """Everything about a host call that does not change from step to step, built once per (dtype, sample_next): the
+        filled ``spl_host_io`` and the result tuple (views of the persistent arrays).  The per-step Python cost of
+        ``step_host`` is then three field writes and one foreign call."""
+        H = self._host_setup(obs_dtype)
+        plan = H["plans"].get((obs_dtype, sample_next))
+        if plan is None:
+            io = L.SplHostIO()
+            obs = H["obs"]
+            io.obs = obs.data_ptr() if obs_dtype == torch.int32 else None
+            io.obs_u8 = obs.data_ptr() if obs_dtype == torch.uint8 else None
+            io.mask, io.reward = H["mask"].data_ptr(), H["reward"].data_ptr()
+            io.terminated, io.info = H["terminated"].data_ptr(), H["info_bits"].data_ptr()
+            io.next_action = H["next_action"].data_ptr() if sample_next else None
+            io.stats = self.stats.data_ptr()
+            io.action_key = self.action_key
+            info = {"action_mask": H["mask"], "to_play": obs[:, 294], "info_bits": H["info_bits"]}
+            if sample_next:
+                info["next_action"] = H["next_action"]
+            plan = dict(io=io, io_ref=C.byref(io), obs=obs, info=info,
+                        step_out=(obs, H["reward"], H["terminated"].view(torch.bool), H["truncated"], info))
+            H["plans"][(obs_dtype, sample_next)] = plan
+        H["obs"] = plan["obs"]
+        return H, plan
+
+    def _host_call(self, fn, name, plan, H, actions_ptr, action_t, autoreset):
+        io = plan["io"]
+        io.actions = actions_ptr
+        io.action_t = action_t
+        io.autoreset = int(autoreset)
+        if torch.cuda.current_device() == self._device_index:
+            rc = fn(H["handle"], self._envs_ref, plan["io_ref"], torch._C._cuda_getCurrentRawStream(self._device_index))
+        else:
+            with torch.cuda.device(self.device):
+                rc = fn(H["handle"], self._envs_ref, plan["io_ref"], self._stream())
+        if rc != 0:
+            L.check(rc, name)
 
     def reset_host(self, *, obs_dtype=torch.int32, sample_next: bool = False, **kw):
         """``reset`` returning HOST tensors -> (obs [N,297], {"action_mask": int8 [N,45], "to_play": ...})."""
         if obs_dtype not in (torch.int32, torch.uint8):
             raise ValueError("obs_dtype must be torch.int32 or torch.uint8")
         self.reset(**kw)
-        self._host_setup(obs_dtype)["io"].action_t = self._t
-        H = self._host_call(self.lib.spl_host_observe, "spl_host_observe", None, obs_dtype, sample_next, False)
-        return H["obs"], {"action_mask": H["mask"], "to_play": H["obs"][:, 294]}
+        H, plan = self._host_plan(obs_dtype, sample_next)
+        self._host_call(self.lib.spl_host_observe, "spl_host_observe", plan, H, None, self._t, False)
+        return plan["obs"], {"action_mask": H["mask"], "to_play": plan["obs"][:, 294]}
 
     def step_host(self, actions, *, obs_dtype=torch.int32, sample_next: bool = False, autoreset: Optional[bool] = None):
         """``SplendorEnv.step`` for every env with HOST arrays in and out -- the call a NumPy-side vector loop makes
         (ppo_splendor.py:235-285).  ``actions``: int32 ``numpy.ndarray`` / CPU tensor ``[N]``.  Returns CPU tensors
         ``(obs, reward, terminated, truncated, info)`` owned by the env and overwritten by the next call;
         ``info["next_action"]`` (with ``sample_next``) is a uniform random legal action per env for the new mask.
-        Device work: H2D actions -> step kernel (compact outputs) -> chunked D2H; host threads widen chunk c into the
-        reference-typed arrays while chunk c+1 is in flight (csrc/spl_host.cu).  Values are those of ``step``."""
+        Device work: H2D actions -> step kernel (compact outputs) -> push kernel, which stores 64-env groups over PCIe
+        into pinned host memory: nibble-packed for the share that pinned host threads widen into the reference-typed
+        arrays, already widened for the rest (csrc/spl_host.cu).  Values are those of ``step``."""
         assert self._is_reset, "Call reset() first"
-        if obs_dtype not in (torch.int32, torch.uint8):
+        if obs_dtype is not torch.int32 and obs_dtype is not torch.uint8:
             raise ValueError("obs_dtype must be torch.int32 or torch.uint8")
         autoreset = self.autoreset if autoreset is None else autoreset
         if autoreset and self.shuffle_mode != L.SHUFFLE_PHILOX and self.spare is None:
             raise L.SplendorB200Error("step_host with auto-reset needs shuffle='philox' or shuffle='mt19937' with prefetch_deals "
                                       "(resets must happen inside the step kernel)")
-        a = torch.as_tensor(actions)
-        if a.dtype != torch.int32 or not a.is_contiguous() or a.device.type != "cpu":
-            a = a.to(device="cpu", dtype=torch.int32).contiguous()
-        if a.numel() != self.n:
-            raise ValueError("actions must have one entry per env")
-        self._host_setup(obs_dtype)["io"].action_t = self._t + 1
-        H = self._host_call(self.lib.spl_host_step, "spl_host_step", a.data_ptr(), obs_dtype, sample_next, autoreset)
+        if isinstance(actions, torch.Tensor):
+            a = actions
+            if a.dtype != torch.int32 or not a.is_contiguous() or a.device.type != "cpu":
+                a = a.to(device="cpu", dtype=torch.int32).contiguous()
+            if a.numel() != self.n:
+                raise ValueError("actions must have one entry per env")
+            ptr = a.data_ptr()
+        else:
+            import numpy as np
+
+            a = actions
+            if not (isinstance(a, np.ndarray) and a.dtype == np.int32 and a.flags.c_contiguous):
+                a = np.ascontiguousarray(actions, dtype=np.int32)
+            if a.size != self.n:
+                raise ValueError("actions must have one entry per env")
+            ptr = a.__array_interface__["data"][0]
+        H, plan = self._host_plan(obs_dtype, sample_next)
+        self._host_call(self.lib.spl_host_step, "spl_host_step", plan, H, ptr, self._t + 1, autoreset)
         self._t += 1
-        info = {"action_mask": H["mask"], "to_play": H["obs"][:, 294], "info_bits": H["info_bits"]}
-        if sample_next:
-            info["next_action"] = H["next_action"]
-        return H["obs"], H["reward"], H["terminated"].view(torch.bool), H["truncated"], info
+        return plan["step_out"]
 
     def close_host(self) -> None:
         H = getattr(self, "_host", None)
         if H is not None:
             self.lib.spl_host_destroy(H["handle"])
+            for k in [k for k, v in H.items() if isinstance(v, torch.Tensor)]:
+                del H[k]  # views over the blocks freed below
+            for ptr in H["blocks"]:
+                self.lib.spl_host_free(ptr)
             self._host = None
+
+    def host_stats(self) -> dict:
+        """Timings of the last ``step_host`` / ``reset_host`` (``spl_host_get_stats``), microseconds from the start of the call."""
+        out = (C.c_double * 8)()
+        L.check(self.lib.spl_host_get_stats(self._host["handle"], out), "spl_host_get_stats")
+        keys = ("call_us", "enqueued_us", "first_group_us", "workers_done_us", "gpu_share_done_us", "gpu_written_share", "threads", "gpu_writable")
+        return dict(zip(keys, [float(v) for v in out]))
 
     def observe(self, out_obs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None):
         """encode_observation + legal_moves of the current states (no step)."""

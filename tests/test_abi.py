@@ -25,7 +25,7 @@ def lib():
 def declared_functions():
     text = open(os.path.join(ROOT, "include", "splendor_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"^\s*(?:const\s+char\s*\*|int64_t|int)\s*\*?\s*(spl_[a-z_0-9]+)\s*\(", text, flags=re.M)
+    names = re.findall(r"^\s*(?:const\s+char\s*\*|int64_t|int|double)\s*\*?\s*(spl_[a-z_0-9]+)\s*\(", text, flags=re.M)
     return sorted(set(names))
 
 

@@ -343,6 +343,7 @@ def test_step_host_equals_step(n, obs_dtype, shuffle):
     assert torch.equal(oa.cpu().to(dt), ob) and torch.equal(ia["action_mask"].cpu(), ib["action_mask"])
     act = a.sample_random_actions().clone()
     assert torch.equal(act.cpu(), b._host["next_action"])
+    assert b.host_stats()["gpu_writable"] == 1.0  # the result arrays come from spl_host_alloc
     rng = torch.Generator().manual_seed(0)
     for t in range(70 if shuffle == "philox" else 200):
         if t % 9 == 4:  # sprinkle illegal / out-of-range actions
@@ -360,6 +361,85 @@ def test_step_host_equals_step(n, obs_dtype, shuffle):
     assert torch.equal(a.export_state(), b.export_state()) and torch.equal(a.stats, b.stats)
     assert int(a.stats[0]) > 0 or n < 100
     b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("direct,nibbles,threads", [("0", "1", 3), ("0.5", "1", 2), ("1", "1", 1), ("0.25", "0", 5), ("0", "0", 1)])
+def test_step_host_shares_and_transfer_forms(direct, nibbles, threads, monkeypatch):
+    """Whatever the split between the GPU-written (already widened) share and the share host threads widen, and whether
+    the staged observation travels nibble-packed or raw, the host arrays hold exactly what step() returns.  Includes a
+    partial last group (n % 64 != 0) and hand-built states whose token counts do not fit a nibble (raw fallback per group)."""
+    import torch
+    from splendor_gym_b200 import SplendorVecEnv
+
+    monkeypatch.setenv("SPL_HOST_DIRECT", direct)
+    monkeypatch.setenv("SPL_HOST_NIBBLES", nibbles)
+    n = 64 * 37 + 21
+    a = SplendorVecEnv(n, seed=9, shuffle="philox", autoreset=True)
+    b = SplendorVecEnv(n, seed=9, shuffle="philox", autoreset=True)
+    b.lib.spl_host_set_threads(threads)
+    a.reset()
+    b.reset()
+    rows = a.export_state()
+    big = torch.arange(0, n, 97, device=rows.device)
+    rows[big, 0] = 20          # bank white = 20: observation entry 0 does not fit a nibble
+    rows[big[::2], 6] = 17     # and 17 white tokens in the mover's hand
+    a.import_state(rows)
+    b.import_state(rows)
+    act = a.sample_random_actions().clone()
+    for t in range(12):
+        o1, r1, t1, _, i1 = a.step(act, sample_next=True)
+        o2, r2, t2, tr2, i2 = b.step_host(act.cpu().numpy().copy(), sample_next=True)
+        assert torch.equal(o1.cpu(), o2), f"step {t}: obs"
+        assert torch.equal(i1["action_mask"].cpu(), i2["action_mask"]), f"step {t}: mask"
+        assert torch.equal(r1.cpu(), r2) and torch.equal(t1.cpu(), t2)
+        assert torch.equal(a.info_bits.cpu(), i2["info_bits"]) and torch.equal(a.next_action.cpu(), i2["next_action"])
+        st = b.host_stats()
+        assert abs(st["gpu_written_share"] - float(direct)) < 0.02 and st["threads"] <= threads
+        act = a.next_action.clone()
+    assert (o2[:, 0] >= 16).any(), "the hand-built wide entries should still be on the table"
+    b.lib.spl_host_set_threads(0)
+    b.close()
+
+
+@pytest.mark.gpu
+def test_step_host_into_plain_arrays():
+    """Result arrays that the GPU cannot write (ordinary pageable memory handed to the C ABI directly): everything is
+    widened by host threads, same values."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from splendor_gym_b200 import SplendorVecEnv, _lib as L
+
+    n = 3000
+    a = SplendorVecEnv(n, seed=2, shuffle="philox", autoreset=True)
+    b = SplendorVecEnv(n, seed=2, shuffle="philox", autoreset=True)
+    a.reset()
+    b.reset()
+    handle = C.c_void_p()
+    L.check(b.lib.spl_host_create(n, 0, C.byref(handle)))
+    obs = np.zeros((n, 297), np.int32)
+    mask = np.zeros((n, 45), np.int8)
+    rew = np.zeros(n, np.float32)
+    term = np.zeros(n, np.uint8)
+    nxt = np.zeros(n, np.int32)
+    io = L.SplHostIO()
+    io.obs, io.mask, io.reward, io.terminated, io.next_action = obs.ctypes.data, mask.ctypes.data, rew.ctypes.data, term.ctypes.data, nxt.ctypes.data
+    io.action_key, io.autoreset = b.action_key, 1
+    act = a.sample_random_actions().clone()
+    for t in range(10):
+        h_act = act.cpu().numpy().copy()
+        io.actions, io.action_t = h_act.ctypes.data, t + 1
+        o1, r1, t1, _, i1 = a.step(act, sample_next=True)
+        L.check(b.lib.spl_host_step(handle, C.byref(b._envs), C.byref(io), b._stream()))
+        assert np.array_equal(o1.cpu().numpy(), obs) and np.array_equal(i1["action_mask"].cpu().numpy(), mask)
+        assert np.array_equal(r1.cpu().numpy(), rew) and np.array_equal(t1.cpu().numpy().astype(np.uint8), term)
+        assert np.array_equal(a.next_action.cpu().numpy(), nxt)
+        st = (C.c_double * 8)()
+        b.lib.spl_host_get_stats(handle, st)
+        assert st[7] == 0.0 and st[5] == 0.0
+        act = a.next_action.clone()
+    b.lib.spl_host_destroy(handle)
 
 
 @pytest.mark.gpu
