@@ -32,6 +32,19 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
 
+def workload_config(N: int, T: int, write_obs: bool = True) -> dict:
+    """`config` of the JSON line: the workload only, so that both arms (--impl b200 / reference) print the same object."""
+    per_step_bytes = N * ((1188 if write_obs else 0) + 45 + 4 + 1 + 4)
+    return {
+        "workload": ("2-player random-legal lock-step rollout, %d envs per GPU (BASELINE configs[1]%s), step+mask+obs+same-step auto-reset"
+                     % (N, "" if N == 65536 else "; envs overridden")) if write_obs else
+                    "simplified take-3 rules, mask+step only (BASELINE configs[3]), %d envs per GPU" % N,
+        "envs_per_gpu": N, "lock_steps_per_step": T,
+        "l2": "results of one step (%.1f GB per GPU: [lock_steps, envs, ...] rollout buffers) are larger than the 126 MB L2; no flush"
+              % (T * per_step_bytes / 1e9),
+    }
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -50,6 +63,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="do not run the bounded sub-results for BASELINE configs 3 / 4 / 5")
     ap.add_argument("--stats-every", type=int, default=1, help="multi-GPU: all-reduce the episode statistics every M bench steps")
     return ap.parse_args()
 
@@ -201,32 +215,186 @@ def run_reference(args):
     O.set_num_threads(host_threads())
     nthreads = O.num_threads()
     envs = args.envs
-    chunk = 8  # lock-steps per bench step: a bounded sample of the rollout segment
+    per_step_bytes = envs * (1188 + 45 + 4 + 1 + 4)
+    T_seg = max(1, min(args.rollout, int(40e9 // per_step_bytes)))  # (the GPU arm's cap on the rollout buffer)
     v = O.OracleVec(envs, seed_base=0)
     v.reset()
+    # one bench step = the GPU arm's step: one segment of T_seg lock-steps of all envs (~0.8 s on 16 cores at the defaults).
+    # Warm-up steps are shortened to 8 lock-steps (they only have to touch the pages and spin up the threads).
     T = 0
     for _ in range(max(args.warmup, 1)):
-        v.rollout_random(0xB200, T, chunk)
-        T += chunk
+        v.rollout_random(0xB200, T, 8)
+        T += 8
     t0 = time.perf_counter()
     done = 0
     for _ in range(args.steps):
-        done += v.rollout_random(0xB200, T, chunk)
-        T += chunk
+        done += v.rollout_random(0xB200, T, T_seg)
+        T += T_seg
     el = time.perf_counter() - t0
     val = done / el
-    sample = f"{envs} envs x {chunk} lock-steps per step (of the {args.rollout}-step segment), oracle C port, {nthreads} threads"
+    sample = f"{envs} envs x {T_seg} lock-steps per step x {args.steps} steps ({done} env-steps, {el:.1f} s), oracle C port of the reference engine, {nthreads} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
-        "config": {"workload": f"2-player random-legal lock-step rollout, {envs} envs (BASELINE configs[1]) on host CPU",
-                   "envs": envs, "lock_steps_per_step": chunk},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "config": workload_config(envs, T_seg),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample,
+                         "python_reference": python_reference_record()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def python_reference_record():
+    """Throughput of the UNMODIFIED Python engine (north_star's named baseline: SplendorEnv under gymnasium's Sync / Async
+    vector env), measured by oracle/time_pyref.py in the build container -- /root/reference cannot travel to the GPU box --
+    and committed as tests/golden/pyref_throughput.json.  Another box: shown next to, never instead of, the same-box port."""
+    p = os.path.join(ROOT, "tests", "golden", "pyref_throughput.json")
+    try:
+        with open(p) as f:
+            rec = json.load(f)
+        rec["note"] = "measured in the build container (other box), see 'host'; the port above ran on this box"
+        return rec
+    except Exception:
+        return None
+
+
+
+def extra_configs(args, dev, rank, world, lib, peak, peak_src):
+    """Bounded sub-results for BASELINE configs[2] (PPO-MLP in the loop, 262,144 envs), configs[3] (mask+step only, 1M envs)
+    and configs[4] (1,048,576 envs per GPU x 30 lock-steps, random policy; all ranks, stats all-reduced over NCCL)."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200 import _lib as L
+
+    out = {}
+
+    def rollout_case(n, T, write_obs, reps):
+        env = SplendorVecEnv(n, device=dev, seed=20261018, shuffle="philox", env_offset=rank * n, autoreset=True)
+        obs = torch.zeros((T, n, 297), dtype=torch.int32, device=dev) if write_obs else None
+        mask = torch.zeros((T, n, 45), dtype=torch.int8, device=dev)
+        rew = torch.zeros((T, n), dtype=torch.float32, device=dev)
+        term = torch.zeros((T, n), dtype=torch.uint8, device=dev)
+        act = torch.zeros((T + 1, n), dtype=torch.int32, device=dev)
+        env.t_base = torch.zeros(1, dtype=torch.int64, device=dev)
+        env.reset()
+        env.sample_random_actions(out=act[0])
+        stats = torch.zeros(8, dtype=torch.int64, device=dev)
+
+        def seg():
+            env._t = 0
+            env.rollout_random(T, act[0], obs=obs, mask=mask, reward=rew, terminated=term, next_actions=act)
+            act[0].copy_(act[T])
+            env.t_base += T
+
+        for _ in range(3):
+            seg()
+        torch.cuda.synchronize()
+        L.check(lib.spl_timing_enable(1))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            seg()
+        if world > 1:  # the episode statistics are the only cross-GPU traffic
+            stats.copy_(env.stats)
+            dist.all_reduce(stats)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        tot, cnt = C.c_double(), C.c_int64()
+        L.check(lib.spl_timing_read(C.byref(tot), C.byref(cnt)))
+        L.check(lib.spl_timing_enable(0))
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        plan = (C.c_int32 * 6)()
+        L.check(lib.spl_rollout_plan(n, T, plan))
+        ob = (1188 if write_obs else 0) + 45 + 4 + 1 + 4
+        bytes_per_launch = n * T * ob + n * 132 * int(plan[3])
+        k_ms = tot.value / max(1, cnt.value)
+        ach = bytes_per_launch / (k_ms * 1e-3) / 1e9
+        sv = B_FULL if write_obs else B_MASKSTEP
+        res = {"value": n * T * reps * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "envs_per_gpu": n, "lock_steps_per_launch": T,
+               "launches": reps, "ms_per_launch": ms / reps,
+               "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "kernel": "spl_rollout_kernel",
+                            "kernel_ms": k_ms, "algorithmic_bytes_per_env_step": bytes_per_launch / (n * T),
+                            "survey_8d_bytes_per_env_step": sv, "frac_with_survey_8d_bytes": n * T * sv / (k_ms * 1e-3) / 1e9 / peak,
+                            "peak_source": peak_src},
+               "episodes": int(stats[0].item()) if world > 1 else int(env.stats[0].item())}
+        env.close()
+        return res
+
+    try:
+        r = rollout_case(1 << 20, 30, False, 10)
+        r["workload"] = "BASELINE configs[3]: mask+step only (no observation encode) at 1,048,576 envs per GPU, random-legal policy, same-step auto-reset"
+        out["config4"] = r
+        torch.cuda.empty_cache()
+        r = rollout_case(1 << 20, 30, True, 10)
+        r["workload"] = ("BASELINE configs[4]: random-policy rollout, 1,048,576 envs per GPU x %d GPU(s) (%d envs), step+mask+obs, episode "
+                         "statistics all-reduced over NCCL" % (world, world << 20))
+        out["config5"] = r
+        torch.cuda.empty_cache()
+    except Exception as ex:  # never lose the headline line to a sub-result
+        out.setdefault("config4", {"error": repr(ex)})
+
+    if world == 1:
+        try:
+            out["config3"] = ppo_case(dev, lib)
+        except Exception as ex:
+            out["config3"] = {"error": repr(ex)}
+    return out
+
+
+def ppo_case(dev, lib, n=262144, steps=6):
+    """BASELINE configs[2]: rollout collection with the reference's ActorCritic MLP in the loop (ppo_splendor.py:202-297,
+    DualStepNativeWrapper turns), env + masked sampling on the device.  agent-steps/s and the env kernels' share of the time."""
+    import ctypes as C
+
+    import torch
+
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200 import _lib as L
+    from splendor_gym_b200.scripts import ppo_rollout as P
+
+    res = {"workload": "BASELINE configs[2]: PPO self-play rollout, ActorCritic MLP (297-256-256-{45,1}, tanh) in the loop, %d envs on 1 GPU; "
+                       "one agent-step = DualStepNativeWrapper.dual_step (agent move + opponent move by the same network)" % n,
+           "unit": "agent-steps/s", "envs": n, "dual_steps_timed": steps}
+    for name, fmt, dt in (("f16", "f16", torch.float16), ("fp32", "int32", torch.float32)):
+        torch.manual_seed(0)
+        net = P.ActorCritic().to(dev).to(dt).eval()
+        if fmt == "f16":
+            net.actor, net.critic = P.pad_head(P.pad_first_layer(net.actor)), P.pad_first_layer(net.critic)
+        env = SplendorVecEnv(n, device=dev, seed=42, shuffle="philox", autoreset=True, obs_format=fmt)
+        env.reset()
+        buf = P.collect(env, net, steps, dtype=dt)
+        torch.cuda.synchronize()
+        L.check(lib.spl_timing_enable(1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        P.collect(env, net, steps, buffers=buf, dtype=dt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        tot, cnt = C.c_double(), C.c_int64()
+        L.check(lib.spl_timing_read(C.byref(tot), C.byref(cnt)))
+        L.check(lib.spl_timing_enable(0))
+        res[name] = {"value": n * steps / (ms * 1e-3), "ms_per_dual_step": ms / steps, "env_step_kernel_ms_per_dual_step": tot.value / steps,
+                     "env_step_kernel_share": tot.value / ms if ms > 0 else None, "policy_dtype": str(dt).replace("torch.", ""),
+                     "obs_format": fmt}
+        env.close()
+        del env, buf, net
+        torch.cuda.empty_cache()
+    res["value"] = res["f16"]["value"]
+    return res
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -598,7 +766,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         v, cores, sample = cpu_rollout(min(N, 65536), args.cpu_seconds)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "python_reference": python_reference_record()}
 
     if world > 1:
         stats_host.copy_(env.stats)
@@ -607,23 +775,29 @@ def run_b200(args):
         stats_host.copy_(env.stats)
     st = stats_host.cpu().tolist()
 
+    # ---- the other BASELINE configs, bounded (a few seconds each), so that the driver's default run carries them
+    extra = {}
+    if not args.skip_configs and write_obs and use_rollout:
+        env.close()
+        del env, obs_buf, mask_buf, rew_buf, term_buf, act_buf
+        torch.cuda.empty_cache()
+        extra = extra_configs(args, dev, rank, world, lib, peak, peak_src)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {
-                "workload": ("2-player random-legal lock-step rollout, %d envs per GPU (BASELINE configs[1]%s), step+mask+obs+same-step auto-reset"
-                             % (N, "" if N == 65536 else "; envs overridden")) if write_obs else
-                            "simplified take-3 rules, mask+step only (BASELINE configs[3]), %d envs per GPU" % N,
-                "envs_per_gpu": N, "lock_steps_per_step": T, "env_steps_per_step": N * T * world, "shuffle": args.shuffle,
+            "config": workload_config(N, T, write_obs),
+            "launch": {
+                "env_steps_per_step": N * T * world, "shuffle": args.shuffle,
                 "mode": "rollout kernel (1 launch per segment)" if use_rollout else "lockstep (1 launch per lock-step)",
                 "rollout_plan": {"warps_per_cta": int(plan[0]), "ctas": int(plan[1]), "lock_steps_per_work_unit": int(plan[2]),
                                  "work_units_per_tile_group": int(plan[3]), "tile_groups": int(plan[5]),
                                  "scheduling": "persistent CTAs pull (tile group, step chunk) units from an atomic queue"},
                 "cuda_graph": graph is not None, "parallelism": f"env-sharded x{world}, no collective on the step path",
-                "l2": "rollout buffer %.1f GB per GPU is larger than the 126 MB L2; no flush" % (T * per_step_bytes / 1e9),
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_u8_obs": e2e_u8, "e2e_plain_copies": e2e_plain, "e2e_device_obs": e2e_light, "lockstep": lockstep,
+            "config3": extra.get("config3"), "config4": extra.get("config4"), "config5": extra.get("config5"),
             "gpu_launches": int(launches_per_segment * K), "clocks": clocks,
             "episode_stats": dict(zip(L.STAT_NAMES, st)),
         }

@@ -70,6 +70,7 @@ extern "C" {
 #define SPL_E_BADARG (-1)
 #define SPL_E_NOTINIT (-2)
 #define SPL_E_ALIGN (-3)
+#define SPL_E_BADROW (-4) /* spl_import_state: a row outside the packed state's domain; such rows are skipped, not truncated */
 
 /* Flat int32 state row (export/import, parity checks): mirrors the reference dataclasses
  * (engine/state.py:52-87) field by field; -1 = None / absent.
@@ -196,7 +197,9 @@ int spl_observe_policy(const spl_envs_t *envs, void *obs_f16, uint8_t *obs_u8, i
 int spl_random_action(const int8_t *mask, int64_t n, uint64_t env_offset, uint64_t key, uint64_t t, int32_t *actions,
                       void *stream);
 
-/* packed state <-> flat int32 rows [n][SPL_ROW_LEN] (device pointers). Import recomputes nothing else. */
+/* packed state <-> flat int32 rows [n][SPL_ROW_LEN] (device pointers). Import recomputes nothing else; it validates every
+ * row (counters < 128, card ids < 90, noble ids < 10, list lengths <= 3, deck sizes within their tier), skips the rows
+ * that fail, waits for the stream and returns SPL_E_BADROW if there were any. */
 int spl_export_state(const spl_envs_t *envs, int32_t *rows, void *stream);
 int spl_import_state(const spl_envs_t *envs, const int32_t *rows, const uint8_t *which, void *stream);
 

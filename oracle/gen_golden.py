@@ -16,6 +16,10 @@ Files written:
   edge_cases.json     hand-built states mirroring the reference's own tests (tests/utils.py style
                       mutation of env.state): full input row, action, and every output
   bots.json           (obs, mask) states + the decisions of the scripted opponents of scripts/eval_suite.py
+  games_digest.json   10,000 reference games under the LCG policy: moves, winner and ONE sha256 per game over every step's
+                      (observation, mask, reward, terminated, info bits)  [python oracle/gen_golden.py games_digest: ~1 min on 8 cores]
+  wrappers.json       SelfPlayWrapper / DualStepNativeWrapper / DualStepSelfPlayWrapper turns (incl. turn-limit draws):
+                      rewards, done flags, opponent moves, observation digests per wrapper step
 """
 from __future__ import annotations
 
@@ -423,12 +427,129 @@ def gen_bots():
     dump("bots.json", out)
 
 
+# ----------------------------------------------------------------------------- games_digest.json
+DIGEST_SEED0, DIGEST_GAMES = 10_000, 10_000
+
+
+def step_record(obs, mask, reward, term, bits) -> bytes:
+    """One step of a game digest: observation as bytes (every entry < 256), mask, float32 reward, terminated, info bits."""
+    o = np.asarray(obs)
+    assert o.max() < 256 and o.min() >= 0
+    return o.astype(np.uint8).tobytes() + np.asarray(mask, np.int8).tobytes() + struct.pack("<fBB", float(reward), int(bool(term)), bits)
+
+
+def lcg_game_digest(seed: int):
+    """The "lcg" policy of play() above; returns (moves, winner or -1, steps, sha256 of all step records)."""
+    env = env_from_state(R.initial_state(seed=seed))
+    x = (seed * 2654435761) % 2**32
+    h = hashlib.sha256()
+    t = 0
+    while True:
+        mask = R.legal_moves(env.state)
+        legal = [i for i, v in enumerate(mask) if v]
+        x = (1664525 * x + 1013904223) % 2**32
+        a = legal[(x >> 16) % len(legal)] if legal else 0
+        obs, r, term, trunc, info = env.step(a)
+        h.update(step_record(obs, info["action_mask"], r, term, info_bits(info, env.state)))
+        t += 1
+        if term or t >= 400:
+            break
+    s = env.state
+    return [s.move_count, -1 if s.winner_index is None else s.winner_index, t, h.hexdigest()[:16]]
+
+
+def gen_games_digest():
+    import multiprocessing as mp
+
+    with mp.get_context("fork").Pool(len(os.sched_getaffinity(0))) as pool:
+        rows = pool.map(lcg_game_digest, range(DIGEST_SEED0, DIGEST_SEED0 + DIGEST_GAMES), chunksize=50)
+    dump("games_digest.json", {
+        "policy": "lcg: x0 = seed * 2654435761 mod 2^32; every step x = 1664525 x + 1013904223 mod 2^32, action = legal[(x >> 16) % len(legal)] (0 if none)",
+        "record": "per step: obs as uint8[297] | mask int8[45] | reward float32 LE | terminated u8 | info bits u8 "
+                  "(1 illegal, 2 draw, 4 turn limit, 8 terminal, (winner + 1) << 4 with final_rewards); sha256 over all steps, first 16 hex digits",
+        "seed0": DIGEST_SEED0, "columns": ["moves", "winner", "steps", "sha"], "games": rows,
+        "env_steps": sum(r[2] for r in rows)})
+
+
+# ----------------------------------------------------------------------------- wrappers.json
+def pick(obs, mask, mul: int, add: int) -> int:
+    """Deterministic stand-in policy, a function of (obs, mask) only: the k-th legal action, k = (sum(obs) * mul + add) mod #legal."""
+    legal = np.flatnonzero(np.asarray(mask))
+    if len(legal) == 0:
+        return 0
+    return int(legal[(int(np.asarray(obs).sum()) * mul + add) % len(legal)])
+
+
+def opponent_det(obs, info):
+    return pick(obs, info["action_mask"], 7, 3)
+
+
+def wrapper_game(kind: str, seed: int, late: bool):
+    from splendor_gym.wrappers.dual_step_native import DualStepNativeWrapper
+    from splendor_gym.wrappers.dual_step_selfplay import DualStepSelfPlayWrapper
+    from splendor_gym.wrappers.selfplay import SelfPlayWrapper
+
+    W = {"selfplay": SelfPlayWrapper, "dual_native": DualStepNativeWrapper, "dual_selfplay": DualStepSelfPlayWrapper}[kind]
+    env = W(ENV.SplendorEnv(), opponent_policy=opponent_det, random_starts=False)
+    obs, info = env.reset(seed=seed)
+    base = env.env
+    if late is True:  # a game that is already at move 190: the turn limit (engine/rules.py:272-277) ends it within a few turns
+        base.state.move_count = 190
+        base.state.turn_count = 96
+        obs, info = ENC.encode_observation(base.state), {"action_mask": np.array(R.legal_moves(base.state), np.int8), "to_play": 0}
+    if late == "stuck":  # the agent has no legal move: empty bank, three unaffordable reserved cards, nothing in hand
+        st = base.state
+        st.players[0].tokens = [0] * 6
+        st.players[0].reserved = [st.decks[3].pop() for _ in range(3)]
+        st.players[1].tokens = [t + b for t, b in zip(st.players[1].tokens, st.bank)]
+        st.bank = [0] * 6
+        obs, info = ENC.encode_observation(st), {"action_mask": np.array(R.legal_moves(st), np.int8), "to_play": 0}
+        assert info["action_mask"].sum() == 0
+    row0 = pyref.state_to_row(base.state).tolist()
+    steps = []
+    t = 0
+    while True:
+        a = pick(obs, info["action_mask"], 5, t)
+        obs, r, term, trunc, info = env.step(a)
+        rec = {"a": a, "r": float(r), "done": bool(term or trunc), "obs": hashlib.sha256(np.asarray(obs, np.int32).tobytes()).hexdigest()[:12],
+               "mask": hashlib.sha256(np.asarray(info["action_mask"], np.int8).tobytes()).hexdigest()[:12],
+               "row": hashlib.sha256(pyref.state_to_row(base.state).tobytes()).hexdigest()[:12]}
+        for k in ("opponent_action", "opponent_reward", "game_ended_on", "phase", "turn_limit", "draw"):
+            if k in info:
+                rec[k] = info[k]
+        if "final_rewards" in info:
+            rec["final_rewards"] = [info["final_rewards"][0], info["final_rewards"][1]]
+        steps.append(rec)
+        t += 1
+        if term or trunc or t >= 300:
+            break
+    out = {"wrapper": kind, "seed": seed, "late": late, "row0": row0, "steps": steps}
+    if hasattr(env, "get_wrapper_stats"):
+        out["stats"] = {k: v for k, v in env.get_wrapper_stats().items() if not isinstance(v, float)}
+    return out
+
+
+def gen_wrappers():
+    out = []
+    for kind in ("selfplay", "dual_native", "dual_selfplay"):
+        for seed in range(300, 310):
+            out.append(wrapper_game(kind, seed, False))
+        for seed in range(320, 326):
+            out.append(wrapper_game(kind, seed, True))
+        out.append(wrapper_game(kind, 330, "stuck"))
+        assert out[-1]["steps"][-1].get("draw") and len(out[-1]["steps"]) == 1
+    limit = [g for g in out if g["steps"][-1].get("turn_limit")]
+    assert len(limit) >= 3, "no turn-limit draw among the late games"
+    # the quirk this fixture pins: a turn-limit draw on the opponent's move is +0.1 under SelfPlayWrapper (selfplay.py:55-57) and
+    # -0.1 under the dual-step wrappers (final_rewards[0], dual_step_selfplay.py:138-152 / dual_step_native.py:159-161)
+    assert any(g["wrapper"] == "selfplay" and g["steps"][-1]["r"] == 0.1 for g in limit)
+    assert any(g["wrapper"] == "dual_selfplay" and g["steps"][-1]["r"] == -0.1 for g in limit)
+    assert any(g["wrapper"] == "dual_native" and g["steps"][-1]["r"] == -0.1 for g in limit)
+    dump("wrappers.json", out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    gen_mt()
-    gen_token_return()
-    gen_initial()
-    gen_env_seeding()
-    gen_games()
-    gen_edges()
-    gen_bots()
+    which = sys.argv[1:] or ["mt", "token_return", "initial", "env_seeding", "games", "edges", "bots", "games_digest", "wrappers"]
+    for name in which:
+        globals()["gen_" + name]()

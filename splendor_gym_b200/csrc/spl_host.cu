@@ -252,6 +252,7 @@ int spl_host_destroy(spl_host_t* h);
 int spl_host_create(int64_t n, int32_t chunks, spl_host_t** out) {
 	(void)chunks;  // kept in the signature (ABI): arrival is tracked per 64-env group now
 	if (n <= 0 || !out) return SPL_E_BADARG;
+	SplRankAffinity on_my_cores;
 	spl_host* h = (spl_host*)calloc(1, sizeof(spl_host));
 	if (!h) return SPL_E_BADARG;
 	h->n = n;
@@ -303,6 +304,7 @@ int spl_host_destroy(spl_host_t* h) {
  * CUDA (pinned + mapped).  Plain host memory to the caller (NumPy / torch can wrap it). */
 int spl_host_alloc(size_t bytes, void** out) {
 	if (!out || bytes == 0) return SPL_E_BADARG;
+	SplRankAffinity on_my_cores;
 	const size_t huge = (size_t)2 << 20;
 	const size_t len = (bytes + huge - 1) / huge * huge;
 	void* p = mmap(nullptr, len + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
@@ -342,10 +344,7 @@ int spl_host_get_stats(const spl_host_t* h, double* out) {
 
 // caller's arrays -> device aliases for the direct share; all requested outputs must be GPU-writable and 16-byte aligned
 static bool resolve_direct(spl_host* h, const spl_host_io_t* io) {
-	if (h->seen_ok != 0 && io->obs == h->seen_io.obs && io->obs_u8 == h->seen_io.obs_u8 && io->mask == h->seen_io.mask &&
-	    io->reward == h->seen_io.reward && io->terminated == h->seen_io.terminated && io->info == h->seen_io.info &&
-	    io->next_action == h->seen_io.next_action)
-		return h->seen_ok > 0;  // 0: nothing resolved yet, 1: GPU-writable, -1: not
+	// looked up on every call (~0.5 us per pointer): an address seen before may have been freed and reused since
 	h->seen_io = *io;
 	PushParams& d = h->seen_dev;
 	memset(&d, 0, sizeof(d));

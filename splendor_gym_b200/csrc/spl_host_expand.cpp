@@ -300,23 +300,51 @@ static void pool_shutdown() {
 	g_pool = nullptr;
 }
 
-// the cores this process may use, rotated so that the ranks of a node (LOCAL_RANK / LOCAL_WORLD_SIZE) take disjoint sets
-static void choose_cpus(SplPool* P) {
-	for (int j = 0; j < SPL_POOL_MAX; j++) P->cpus[j] = -1;
-	if (!g_pin) return;
+// the cores this rank may use: the process's affinity mask, cut into LOCAL_WORLD_SIZE contiguous slices (torchrun:
+// one process per GPU; contiguous core numbers share a socket, and so does the memory their threads touch first)
+static int rank_cpus(int* out, int cap) {
 	cpu_set_t set;
-	if (sched_getaffinity(0, sizeof(set), &set) != 0) return;
+	if (sched_getaffinity(0, sizeof(set), &set) != 0) return 0;
 	int avail[1024], na = 0;
 	for (int c = 0; c < CPU_SETSIZE && na < 1024; c++)
 		if (CPU_ISSET(c, &set)) avail[na++] = c;
-	if (na == 0) return;
+	if (na == 0) return 0;
 	const char* lr = getenv("LOCAL_RANK");
 	const char* lws = getenv("LOCAL_WORLD_SIZE");
 	const int rank = lr ? atoi(lr) : 0, ws = lws && atoi(lws) > 0 ? atoi(lws) : 1;
 	const int per = na / ws > 0 ? na / ws : 1;
-	const int first = (rank % ws) * per;
+	const int first = ((rank % ws) * per) % na;
+	int n = 0;
+	for (int k = 0; k < per && n < cap; k++) out[n++] = avail[(first + k) % na];
+	return n;
+}
+
+static void choose_cpus(SplPool* P) {
+	for (int j = 0; j < SPL_POOL_MAX; j++) P->cpus[j] = -1;
+	if (!g_pin) return;
+	int mine[1024];
+	const int per = rank_cpus(mine, 1024);
+	if (per == 0) return;
 	// worker 0 is the caller's thread and is left where the OS put it; workers 1.. take the rank's cores from the top
-	for (int j = 1; j < P->threads; j++) P->cpus[j] = avail[(first + per - 1 - ((j - 1) % per)) % na];
+	for (int j = 1; j < P->threads; j++) P->cpus[j] = mine[per - 1 - ((j - 1) % per)];
+}
+
+// Run the calling thread on the rank's cores while it allocates and first-touches buffers (several ranks per node only:
+// the pages then land on the memory of the socket whose cores will stream into them), then put its mask back.
+SplRankAffinity::SplRankAffinity() : active(false) {
+	const char* lws = getenv("LOCAL_WORLD_SIZE");
+	if (!g_pin || !lws || atoi(lws) <= 1) return;
+	if (sched_getaffinity(0, sizeof(saved), &saved) != 0) return;
+	int mine[1024];
+	const int per = rank_cpus(mine, 1024);
+	if (per == 0) return;
+	cpu_set_t set;
+	CPU_ZERO(&set);
+	for (int k = 0; k < per; k++) CPU_SET(mine[k], &set);
+	active = sched_setaffinity(0, sizeof(set), &set) == 0;
+}
+SplRankAffinity::~SplRankAffinity() {
+	if (active) sched_setaffinity(0, sizeof(saved), &saved);
 }
 
 // default size of the pool: 3/4 of the cores this rank may use.  Measured (16 vCPUs, tools/microbench/host_bw.c):

@@ -6,6 +6,8 @@
 
 #include <atomic>
 
+#include <sched.h>
+
 #include "../../include/splendor_b200.h"
 
 #define SPL_HOST_GROUP 64  /* envs per arrival flag: 19,008 observation bytes + 1 KB of records */
@@ -38,6 +40,13 @@ struct SplHostJob {
 		abort.store(o.abort.load());
 		return *this;
 	}
+};
+
+struct SplRankAffinity {  // scope guard, see spl_host_expand.cpp
+	cpu_set_t saved;
+	bool active;
+	SplRankAffinity();
+	~SplRankAffinity();
 };
 
 double spl_now_us();

@@ -413,6 +413,7 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 				if (tops != nullptr) *tops = (w8 >> 24) | (((w16 >> 8) & 0xFFu) << 8) | (((w21 >> 8) & 0xFFu) << 16);  // bytes 35, 65, 85
 			}
 		}
+		__syncwarp();  // the deck rows written above (lanes 0..23) are popped by their owning lanes in later steps
 		rb = late;
 		if (rb == 0) return;
 		if (p.reset_mode == SPL_RESET_SPARE_INLINE) {
@@ -1129,9 +1130,14 @@ __global__ void spl_export_kernel(const uint4* state, int64_t stride, const uint
 	spl_export_row(s, decks + env * SPL_DECK_STRIDE, rows + env * SPL_ROW_LEN);
 }
 
-__global__ void spl_import_kernel(uint4* state, int64_t stride, uint8_t* decks, int64_t n, const int32_t* rows, const uint8_t* which) {
+// A row outside the packed state's domain (spl_row_valid) is not imported: its env keeps its state and *bad is bumped.
+__global__ void spl_import_kernel(uint4* state, int64_t stride, uint8_t* decks, int64_t n, const int32_t* rows, const uint8_t* which, int* bad) {
 	int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (env >= n || (which && !which[env])) return;
+	if (!spl_row_valid(rows + env * SPL_ROW_LEN)) {
+		atomicAdd(bad, 1);
+		return;
+	}
 	SplState s;
 	uint32_t w[16];
 	spl_import_row(rows + env * SPL_ROW_LEN, s, decks + env * SPL_DECK_STRIDE);
@@ -1194,6 +1200,20 @@ static int g_ev_created = 0, g_ev_used = 0, g_timing = 0;
 		if (e_ != cudaSuccess) return (int)e_; \
 	} while (0)
 
+// Tuning knobs (environment variables, diagnostics only): read once per spl_init() call, not per launch.
+enum { K_DEAL_BATCH, K_DEAL_MAX_OUTPUTS, K_ROLLOUT_CHUNK, K_ROLLOUT_CTAS_PER_SM, K_ROLLOUT_SYNC, K_SPARE_REFILL_AGE, K_SPARE_WORKLIST, K_STEP_PERSISTENT, K_STEP_WPC, K_WPC, K_COUNT };
+static const char* const g_knob_names[K_COUNT] = {"SPL_DEAL_BATCH", "SPL_DEAL_MAX_OUTPUTS", "SPL_ROLLOUT_CHUNK", "SPL_ROLLOUT_CTAS_PER_SM", "SPL_ROLLOUT_SYNC", "SPL_SPARE_REFILL_AGE", "SPL_SPARE_WORKLIST", "SPL_STEP_PERSISTENT", "SPL_STEP_WPC", "SPL_WPC"};
+static int g_knobs[K_COUNT];
+static bool g_knob_set[K_COUNT];
+static void load_knobs() {
+	for (int k = 0; k < K_COUNT; k++) {
+		const char* e = getenv(g_knob_names[k]);
+		g_knob_set[k] = e && *e;
+		g_knobs[k] = g_knob_set[k] ? atoi(e) : 0;
+	}
+}
+static inline int knob(int k, int dflt) { return g_knob_set[k] ? g_knobs[k] : dflt; }
+
 extern "C" {
 
 int spl_version(void) { return 110; }  // 110: spl_envs.spare_slots, spl_step_io.flags, spl_refill_spares
@@ -1242,6 +1262,7 @@ const char* spl_error_string(int code) {
 	if (code == SPL_E_BADARG) return "splendor_b200: bad argument";
 	if (code == SPL_E_NOTINIT) return "splendor_b200: spl_init() has not been called on this device";
 	if (code == SPL_E_ALIGN) return "splendor_b200: state pointer must be 16-byte aligned";
+	if (code == SPL_E_BADROW) return "splendor_b200: state row outside the engine's domain (counter >= 128, id out of range or list too long); rejected rows were not imported";
 	if (code > 0) return cudaGetErrorString((cudaError_t)code);
 	return "splendor_b200: unknown error";
 }
@@ -1258,6 +1279,7 @@ int spl_host_ret_table(uint64_t* out) {
 int spl_init(void) {
 	int dev = 0;
 	SPL_CUDA(cudaGetDevice(&dev));
+	load_knobs();
 	if (g_inited_device == dev) return 0;
 	SplTables T;
 	spl_build_tables(&T);
@@ -1306,10 +1328,6 @@ static int check_envs(const spl_envs_t* e) {
 	return 0;
 }
 
-static int env_int(const char* name, int dflt) {
-	const char* e = getenv(name);
-	return e ? atoi(e) : dflt;
-}
 
 // what a reset launch does: reset the envs themselves, or (prefetched deals) only deal upcoming episodes into ring slots
 #define SPL_RESET_NORMAL 0
@@ -1331,7 +1349,7 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 	p.n = e->n, p.env_offset = e->env_offset, p.seed_base = e->seed_base, p.seeds = seeds, p.obs = obs, p.mask = mask;
 	p.bump_episode = bump;
 	p.spare_out = nullptr, p.refill = nullptr;
-	p.spare_slots = 1, p.list_is_envs = 0, p.max_outputs = env_int("SPL_DEAL_MAX_OUTPUTS", 227);
+	p.spare_slots = 1, p.list_is_envs = 0, p.max_outputs = knob(K_DEAL_MAX_OUTPUTS, 227);
 	int64_t groups = (e->n + 31) / 32;
 	if (kind != SPL_RESET_NORMAL) {
 		if (e->shuffle_mode != SPL_SHUFFLE_MT19937 || e->spare == nullptr) return SPL_E_BADARG;
@@ -1348,7 +1366,7 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 			SPL_CUDA(cudaGetLastError());
 		}
 	}
-	if (kind != SPL_RESET_NORMAL && env_int("SPL_DEAL_BATCH", 1) != 0) {
+	if (kind != SPL_RESET_NORMAL && knob(K_DEAL_BATCH, 1) != 0) {
 		// items: every (env, slot) / every slot of the listed envs / the refill list (length known on the device only)
 		int64_t ctas = (e->n * p.spare_slots + SPL_DEAL_THREADS - 1) / SPL_DEAL_THREADS;
 		const int64_t cap = (int64_t)g_num_sms * 12;
@@ -1403,7 +1421,7 @@ static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_
 	p.spare_async = io && (io->flags & SPL_IO_ASYNC_REFILL) ? 1 : 0;
 	if (io && io->autoreset)
 		p.reset_mode = e->shuffle_mode == SPL_SHUFFLE_PHILOX ? SPL_RESET_FUSED
-		             : (e->spare ? (env_int("SPL_SPARE_WORKLIST", 0) ? SPL_RESET_SPARE : SPL_RESET_SPARE_INLINE) : SPL_RESET_WORKLIST);
+		             : (e->spare ? (knob(K_SPARE_WORKLIST, 0) ? SPL_RESET_SPARE : SPL_RESET_SPARE_INLINE) : SPL_RESET_WORKLIST);
 	p.vec_ok = (((uintptr_t)obs | (uintptr_t)mask) & 15) == 0;  // 128-bit tile stores
 	p.steps = 1;
 	p.sync = 0;
@@ -1426,20 +1444,20 @@ static LaunchShape launch_shape(int64_t n, int kernel) {
 	const int64_t ntiles = (n + 31) / 32;
 	LaunchShape L;
 	int64_t resident4 = (int64_t)g_num_sms * g_occ[kernel][1] * 4;
-	L.wpc = kernel != 2 ? env_int("SPL_STEP_WPC", 1) : env_int("SPL_WPC", ntiles <= resident4 ? 1 : 4);
+	L.wpc = kernel != 2 ? knob(K_STEP_WPC, 1) : knob(K_WPC, ntiles <= resident4 ? 1 : 4);
 	if (L.wpc != 1) L.wpc = 4;
 	int64_t ctas = (ntiles + L.wpc - 1) / L.wpc;
 	int64_t cap = (int64_t)g_num_sms * g_occ[kernel][L.wpc == 1 ? 0 : 1];
 	L.grid = (int)(ctas < cap ? ctas : cap);
-	if (kernel != 2 && env_int("SPL_STEP_PERSISTENT", 0) == 0) L.grid = (int)ctas;  // one tile group per CTA: the hardware
+	if (kernel != 2 && knob(K_STEP_PERSISTENT, 0) == 0) L.grid = (int)ctas;  // one tile group per CTA: the hardware
 	                                                                                  // CTA scheduler balances the SMs
 	L.sync = 0;
 	L.chunk = 1;
 	if (kernel == 2) {
-		L.sync = env_int("SPL_ROLLOUT_SYNC", 0);
-		L.chunk = env_int("SPL_ROLLOUT_CHUNK", ctas <= cap ? 8 : 12);  // measured: flat between 8 and 16
+		L.sync = knob(K_ROLLOUT_SYNC, 0);
+		L.chunk = knob(K_ROLLOUT_CHUNK, ctas <= cap ? 8 : 12);  // measured: flat between 8 and 16
 		if (L.chunk < 1) L.chunk = 1;
-		const int per_sm = env_int("SPL_ROLLOUT_CTAS_PER_SM", 0);
+		const int per_sm = knob(K_ROLLOUT_CTAS_PER_SM, 0);
 		if (per_sm > 0) {
 			cap = (int64_t)g_num_sms * per_sm;
 			L.grid = (int)(ctas < cap ? ctas : cap);
@@ -1470,7 +1488,7 @@ static int refill_spares_if_due(const spl_envs_t* envs, const spl_step_io_t* io,
 	// (capped at 64 lock-steps: callers that re-base action_t per rollout segment, e.g. per replayed CUDA graph, then still
 	// reach the cadence inside every segment of 64 x k lock-steps)
 	const int slots = spare_slots(envs) < 4 ? spare_slots(envs) : 4;
-	const int age = env_int("SPL_SPARE_REFILL_AGE", SPL_SPARE_REFILL_AGE * slots);
+	const int age = knob(K_SPARE_REFILL_AGE, SPL_SPARE_REFILL_AGE * slots);
 	if (age <= 1 || io->action_t % (uint64_t)age == 0)
 		return launch_reset(envs, nullptr, nullptr, 0, nullptr, nullptr, st, io, SPL_RESET_SPARE_REFILL_NOW);
 	return 0;
@@ -1533,7 +1551,7 @@ int spl_step(const spl_envs_t* envs, const spl_step_io_t* io, void* stream) {
 	// the step kernel), else finished envs are queued for the reset kernel that follows (624 generator words per env)
 	const bool mt = io->autoreset && envs->shuffle_mode != SPL_SHUFFLE_PHILOX;
 	const bool spares = mt && envs->spare != nullptr;
-	const bool worklist = mt && (!spares || env_int("SPL_SPARE_WORKLIST", 0) != 0);
+	const bool worklist = mt && (!spares || knob(K_SPARE_WORKLIST, 0) != 0);
 	if (worklist) SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, 16, st));
 	if ((io->obs_f16 || io->obs_u8) && worklist) return SPL_E_BADARG;  // the MT19937 reset kernel writes int32 observations only
 	rc = launch_step(envs, io, true, io->obs, io->mask, st, io->obs_f16, io->obs_u8);
@@ -1636,10 +1654,20 @@ int spl_import_state(const spl_envs_t* envs, const int32_t* rows, const uint8_t*
 	int rc = check_envs(envs);
 	if (rc) return rc;
 	if (!rows) return SPL_E_BADARG;
+	// import is not on the step path (tests, debugging, the single-env facade): it waits for the kernel and reports rows it
+	// rejected (counters >= 128, card / noble ids out of range, list lengths > 3 ...) instead of truncating them silently
+	int* bad = nullptr;
+	SPL_CUDA(cudaMallocAsync(&bad, sizeof(int), (cudaStream_t)stream));
+	SPL_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), (cudaStream_t)stream));
 	spl_import_kernel<<<(unsigned)((envs->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)envs->state, envs->stride, envs->decks,
-	                                                                                    envs->n, rows, which);
+	                                                                                    envs->n, rows, which, bad);
 	g_launches++;
-	return (int)cudaGetLastError();
+	SPL_CUDA(cudaGetLastError());
+	int nbad = 0;
+	SPL_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+	SPL_CUDA(cudaFreeAsync(bad, (cudaStream_t)stream));
+	SPL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+	return nbad ? SPL_E_BADROW : 0;
 }
 
 int spl_dual_combine(const float* r1, const uint8_t* term1, const uint8_t* info1, const float* r2, const uint8_t* term2,

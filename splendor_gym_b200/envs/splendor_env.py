@@ -84,6 +84,10 @@ class SplendorEnv(Env):
         mask = vec.mask[0].cpu().numpy().astype(np.int8)
         reward = float(vec.reward[0])
         terminated = bool(vec.terminated[0])
+        return obs, reward, terminated, False, self._info(bits, terminated, mask)
+
+    def _info(self, bits: int, terminated: bool, mask: np.ndarray) -> Dict[str, Any]:
+        """The reference's info dict (envs/splendor_env.py:61,66,81-88) from the kernel's info bits; ``self.state`` is current."""
         info: Dict[str, Any] = {"action_mask": mask, "to_play": int(self.state.to_play)}
         if bits & L.INFO_NOLEGAL_DRAW:
             info["draw"] = True
@@ -93,7 +97,7 @@ class SplendorEnv(Env):
             info["turn_limit"] = True
         if terminated and not (bits & L.INFO_NOLEGAL_DRAW):
             info["final_rewards"] = self.get_final_rewards()
-        return obs, reward, terminated, False, info
+        return info
 
     def get_final_rewards(self) -> Dict[int, float]:
         """envs/splendor_env.py:92-115."""

@@ -70,8 +70,12 @@ def _snapshot(env: SplendorVecEnv):
     return env.state.clone(), env.decks.clone(), env.episode.clone()
 
 
-def record_random(env: SplendorVecEnv, steps: int, seed: int) -> Trajectory:
-    """Random-legal rollout of `steps` lock-steps (one launch); only actions / rewards / terminations are kept."""
+def record_random(env: SplendorVecEnv, steps: int, seed: Optional[int] = None) -> Trajectory:
+    """Random-legal rollout of `steps` lock-steps (one launch); only actions / rewards / terminations are kept.
+    The trajectory records the env's OWN base seed (auto-reset deals are a function of it); ``seed`` is accepted for
+    backwards compatibility and must agree with it."""
+    if seed is not None and int(seed) != int(env._envs.seed_base):
+        raise ValueError("record_random: seed differs from the env's base seed (the replay would deal other decks)")
     n, dev = env.n, env.device
     st, dk, ep = _snapshot(env)
     acts = torch.zeros((steps + 1, n), dtype=torch.int32, device=dev)
@@ -80,7 +84,7 @@ def record_random(env: SplendorVecEnv, steps: int, seed: int) -> Trajectory:
     env.sample_random_actions(out=acts[0])
     env.rollout_random(steps, acts[0], obs=None, mask=None, reward=rew, terminated=term, next_actions=acts)
     shuffle = "philox" if env.shuffle_mode == 1 else "mt19937"
-    return Trajectory(seed, int(env._envs.env_offset), shuffle, st, dk, ep, acts[:steps].clone(), rew, term)
+    return Trajectory(int(env._envs.seed_base), int(env._envs.env_offset), shuffle, st, dk, ep, acts[:steps].clone(), rew, term)
 
 
 def replay(traj: Trajectory, device="cuda", sink: Optional[Callable[[int, torch.Tensor, torch.Tensor], None]] = None,

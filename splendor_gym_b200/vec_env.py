@@ -181,6 +181,9 @@ class SplendorVecEnv:
               reset_mask: Optional[torch.Tensor] = None, options=None):
         """``SplendorEnv.reset`` for all envs (or those flagged in ``reset_mask``) -> (obs, info)."""
         if seed is not None:
+            if reset_mask is not None and int(seed) != int(self._envs.seed_base):
+                # the prefetched deals of the envs that are NOT reset were computed from the current base seed
+                raise ValueError("reset(seed=...) re-seeds every env: it cannot be combined with reset_mask")
             self._envs.seed_base = int(seed)
         if seeds is not None:
             seeds = seeds.to(device=self.device, dtype=torch.int64).contiguous()

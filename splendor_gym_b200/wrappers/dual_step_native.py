@@ -1,80 +1,54 @@
-"""DualStepNativeWrapper (splendor_gym/wrappers/dual_step_native.py:6-223): `dual_step(a)` = the agent's move,
-the opponent policy's move, both rewards.  The batched equivalent is `SplendorVecEnv.dual_step`."""
+"""DualStepNativeWrapper (splendor_gym/wrappers/dual_step_native.py:6-223): ``dual_step(a)`` = the agent's move, the
+opponent policy's reply, both players' rewards.  An adapter: the turn is one ``SplendorVecEnv(1).dual_step`` on the
+device (``_turn.play_turn``); the batched form for many envs is ``SplendorVecEnv.dual_step`` itself."""
 from __future__ import annotations
 
-from typing import Any, Callable, Dict, Optional, Tuple
+from typing import Any, Dict, Tuple
 
 import numpy as np
 
-from ..envs._gym_compat import Wrapper
-from .selfplay import random_opponent  # noqa: F401  (re-exported like the reference, :214-223)
+from ._turn import play_turn
+from .selfplay import _OpponentSeat, random_opponent  # noqa: F401  (random_opponent is re-exported like the reference, :214-223)
 
 
-class DualStepNativeWrapper(Wrapper):
-    def __init__(self, env, opponent_policy: Callable, random_starts: bool = True, opponent_supplier: Optional[Callable] = None):
-        super().__init__(env)
-        self.opponent_policy = opponent_policy
-        self.random_starts = random_starts
-        self.opponent_supplier = opponent_supplier
-        self._opp_policy = opponent_policy
-        self.turn_count = 0
-        self.total_agent_steps = 0
-        self.total_opponent_steps = 0
+class DualStepNativeWrapper(_OpponentSeat):
+    def __init__(self, env, opponent_policy, random_starts: bool = True, opponent_supplier=None):
+        super().__init__(env, opponent_policy, random_starts, opponent_supplier)
+        self.turn_count = self.total_agent_steps = self.total_opponent_steps = 0
+
+    def _opponent_moved(self) -> None:
+        self.total_opponent_steps += 1
 
     def reset(self, **kwargs):
-        self._opp_policy = self.opponent_supplier() if self.opponent_supplier is not None else self.opponent_policy
-        obs, info = self.env.reset(**kwargs)
         self.turn_count = self.total_agent_steps = self.total_opponent_steps = 0
-        if self.random_starts and info.get("to_play", 0) == 1 and np.random.rand() < 0.5:
-            obs, _, term, trunc, info = self.env.step(self._opp_policy(obs, info))
-            self.total_opponent_steps += 1
-            if term or trunc:
-                return obs, info
-        while info.get("to_play", 0) == 1:
-            obs, _, term, trunc, info = self.env.step(self._opp_policy(obs, info))
-            self.total_opponent_steps += 1
-            if term or trunc:
-                break
-        return obs, info
+        return super().reset(**kwargs)
 
     def step(self, action: int):
-        agent_obs, agent_reward, _, _, done, info = self.dual_step(action)
-        return agent_obs, agent_reward, done, False, info
-
-    @staticmethod
-    def _final_reward(info: Dict, player_id: int) -> float:
-        fr = info.get("final_rewards")
-        return fr[player_id] if fr is not None and player_id in fr else 0.0
+        obs, reward, _, _, done, info = self.dual_step(action)
+        return obs, reward, done, False, info
 
     def dual_step(self, agent_action: int) -> Tuple[np.ndarray, float, np.ndarray, float, bool, Dict[str, Any]]:
-        if getattr(self.env, "state", None) is None:
+        """-> (agent_obs, agent_reward, opponent_obs, opponent_reward, done, info); both observations are the position
+        after the turn (:182-191); the agent's reward of a finished game is final_rewards[0] (:159-161)."""
+        state = getattr(self.env, "state", None)
+        if state is None:
             raise RuntimeError("Cannot call dual_step() before reset()")
-        if self.env.state.to_play != 0:
+        if state.to_play != 0:
             raise ValueError("dual_step() requires agent (player 0) to move first")
+        turn = play_turn(self.env, agent_action, self._opp_policy, "native")
+        if not turn.done and turn.opponent_action is None:
+            raise ValueError(f"Expected opponent (player 1) to move after agent, got to_play={turn.info_agent.get('to_play')}")
         self.turn_count += 1
         self.total_agent_steps += 1
-        obs1, r1, done1, trunc1, info1 = self.env.step(agent_action)
-        turn_info = {"turn_count": self.turn_count, "agent_action": agent_action, "total_agent_steps": self.total_agent_steps,
-                     "total_opponent_steps": self.total_opponent_steps, "phase": "agent_only"}
-        turn_info.update(info1)
-        if done1 or trunc1:
-            opp_r = self._final_reward(info1, 1)
-            turn_info.update({"opponent_action": None, "opponent_reward": opp_r, "turn_complete": True, "game_ended_on": "agent_move"})
-            return obs1, r1, obs1, opp_r, True, turn_info
-        if self.env.state.to_play != 1:
-            raise ValueError(f"Expected opponent (player 1) to move after agent, got to_play={self.env.state.to_play}")
-        opp_action = self._opp_policy(obs1, info1)
-        self.total_opponent_steps += 1
-        obs2, r2, done2, trunc2, info2 = self.env.step(opp_action)
-        ended = done2 or trunc2
-        agent_r = self._final_reward(info2, 0) if ended else 0.0
-        turn_info.update(info2)
-        turn_info.update({"opponent_action": opp_action, "opponent_reward": r2, "total_opponent_steps": self.total_opponent_steps,
-                          "phase": "complete_turn", "turn_complete": True, "game_ended_on": "opponent_move" if ended else None})
-        return obs2, agent_r, obs2, r2, ended, turn_info
+        replied = turn.opponent_action is not None
+        self.total_opponent_steps += int(replied)
+        info: Dict[str, Any] = {"turn_count": self.turn_count, "agent_action": agent_action, "total_agent_steps": self.total_agent_steps}
+        info.update(turn.info_agent)
+        info.update(turn.info_final)
+        info.update(total_opponent_steps=self.total_opponent_steps, phase="complete_turn" if replied else "agent_only",
+                    opponent_action=turn.opponent_action, opponent_reward=turn.opponent_reward, turn_complete=True, game_ended_on=turn.ended_on)
+        return turn.obs, turn.agent_reward, turn.obs, turn.opponent_reward, turn.done, info
 
     def get_wrapper_stats(self) -> Dict[str, Any]:
-        return {"turn_count": self.turn_count, "total_agent_steps": self.total_agent_steps,
-                "total_opponent_steps": self.total_opponent_steps,
-                "avg_opponent_steps_per_turn": self.total_opponent_steps / max(1, self.turn_count),
-                "wrapper_type": "DualStepNativeWrapper"}
+        return dict(turn_count=self.turn_count, total_agent_steps=self.total_agent_steps, total_opponent_steps=self.total_opponent_steps,
+                    avg_opponent_steps_per_turn=self.total_opponent_steps / max(1, self.turn_count), wrapper_type="DualStepNativeWrapper")

@@ -281,6 +281,92 @@ def test_selfplay_and_dual_step_wrappers_against_batched_path():
         assert all(x[3] for x in singles)
 
 
+def _det_pick(obs, mask, mul, add):
+    """oracle/gen_golden.py:pick -- k-th legal action with k = (sum(obs) * mul + add) mod #legal (what the fixture's players do)."""
+    legal = np.flatnonzero(np.asarray(mask))
+    return 0 if len(legal) == 0 else int(legal[(int(np.asarray(obs).sum()) * mul + add) % len(legal)])
+
+
+def _sha12(a, dtype):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype).tobytes()).hexdigest()[:12]
+
+
+def test_wrappers_match_reference_generated_turns():
+    """tests/golden/wrappers.json was produced by the reference's SelfPlayWrapper / DualStepNativeWrapper /
+    DualStepSelfPlayWrapper (51 games incl. turn-limit draws -- +0.1 under SelfPlayWrapper, -0.1 under the dual-step wrappers
+    -- and a no-legal-move draw on the agent's move).  The three single-env wrappers here (adapters over the device turn) must
+    return the same observation, mask, reward, done flag, opponent move / reward and bookkeeping at every step."""
+    from splendor_gym_b200.engine.state import row_to_state, state_to_row
+    from splendor_gym_b200.envs import SplendorEnv
+    from splendor_gym_b200.wrappers import DualStepNativeWrapper, DualStepSelfPlayWrapper, SelfPlayWrapper
+
+    kinds = {"selfplay": SelfPlayWrapper, "dual_native": DualStepNativeWrapper, "dual_selfplay": DualStepSelfPlayWrapper}
+    seen_rewards = set()
+    for g in load_golden("wrappers.json"):
+        env = kinds[g["wrapper"]](SplendorEnv(), opponent_policy=lambda o, i: _det_pick(o, i["action_mask"], 7, 3), random_starts=False)
+        env.reset(seed=g["seed"])
+        env.env.state = row_to_state(np.array(g["row0"], np.int32))
+        for t, want in enumerate(g["steps"]):
+            obs, r, done, trunc, info = env.step(want["a"])
+            where = (g["wrapper"], g["seed"], t)
+            assert r == pytest.approx(want["r"]) and done == want["done"] and trunc is False, where
+            assert _sha12(obs, np.int32) == want["obs"] and _sha12(info["action_mask"], np.int8) == want["mask"], where
+            assert _sha12(state_to_row(env.env.state), np.int32) == want["row"], where
+            for k in ("opponent_action", "game_ended_on", "phase", "turn_limit", "draw"):
+                if k in want:
+                    assert info.get(k) == want[k], (where, k)
+                elif k in ("turn_limit", "draw"):
+                    assert k not in info, (where, k)
+            if "opponent_reward" in want:
+                assert info["opponent_reward"] == pytest.approx(want["opponent_reward"]), where
+            if "final_rewards" in want:
+                assert [info["final_rewards"][0], info["final_rewards"][1]] == pytest.approx(want["final_rewards"]), where
+            if done:
+                seen_rewards.add((g["wrapper"], round(float(r), 2), bool(want.get("turn_limit"))))
+        assert done
+        if "stats" in g:
+            st = env.get_wrapper_stats()
+            assert {k: st[k] for k in g["stats"]} == g["stats"]
+    assert ("selfplay", 0.1, True) in seen_rewards and ("dual_selfplay", -0.1, True) in seen_rewards and ("dual_native", -0.1, True) in seen_rewards
+
+
+def test_batched_dual_step_matches_reference_generated_turns():
+    """The same fixture through the BATCHED path: all 51 games side by side in one SplendorVecEnv, a turn =
+    dual_step(reward_mode=...) with the opponent's deterministic policy evaluated on the device."""
+    from splendor_gym_b200 import SplendorVecEnv
+
+    for mode, kinds in (("selfplay", ("selfplay",)), ("native", ("dual_native", "dual_selfplay"))):
+        games = [g for g in load_golden("wrappers.json") if g["wrapper"] in kinds]
+        n = len(games)
+        vec = SplendorVecEnv(n, shuffle="mt19937", autoreset=False)
+        vec.reset()
+        vec.import_state(torch.tensor([g["row0"] for g in games], dtype=torch.int32))
+        moves = {}
+
+        def opponent(obs, mask):
+            cnt = mask.sum(1, dtype=torch.int64)
+            k = (obs.sum(1, dtype=torch.int64) * 7 + 3) % cnt.clamp(min=1)
+            a = (mask.to(torch.int64).cumsum(1) > k[:, None]).to(torch.uint8).argmax(1).to(torch.int32)
+            a[cnt == 0] = 0
+            moves["opp"] = a
+            return a
+
+        for t in range(max(len(g["steps"]) for g in games)):
+            live = [t < len(g["steps"]) for g in games]
+            acts = torch.tensor([g["steps"][t]["a"] if live[i] else 0 for i, g in enumerate(games)], dtype=torch.int32, device=vec.device)
+            obs, agent_r, _, opp_r, done, info = vec.dual_step(acts, opponent, reward_mode=mode)
+            o, m, rows = obs.cpu().numpy(), info["action_mask"].cpu().numpy(), vec.export_state().cpu().numpy()
+            for i, g in enumerate(games):
+                if not live[i]:
+                    continue
+                want = g["steps"][t]
+                where = (mode, g["wrapper"], g["seed"], t)
+                assert float(agent_r[i]) == pytest.approx(want["r"]) and bool(done[i]) == want["done"], where
+                assert _sha12(o[i], np.int32) == want["obs"] and _sha12(m[i], np.int8) == want["mask"] and _sha12(rows[i], np.int32) == want["row"], where
+                if want.get("opponent_action") is not None:
+                    assert int(moves["opp"][i]) == want["opponent_action"] and float(opp_r[i]) == pytest.approx(want["opponent_reward"]), where
+
+
 def test_random_opponent_helper():
     from splendor_gym_b200.wrappers import random_opponent
 

@@ -670,3 +670,82 @@ def test_unaligned_output_buffers_and_strided_state(VecEnv, oracle):
     assert int(big_mask[:3].abs().sum()) == 0 and int(big_mask[3 + n * 45:].abs().sum()) == 0
     rows = _np(env.export_state())[:n]
     assert np.array_equal(rows, ref.export_rows())
+
+
+def test_ten_thousand_reference_games_by_digest(VecEnv):
+    """CUDA directly against the reference at volume: the 10,000 games of tests/golden/games_digest.json (773,764 env-steps
+    played by the unmodified Python engine under the LCG policy) replayed on the GPU, one env per game, in lock-step.
+    The policy runs on the device from the kernel's own masks; every step's observation, mask, reward, terminated flag and
+    info bits go into the game's sha256, which must equal the reference's, as must move counts and winners."""
+    import digest_util as D
+
+    G = load_golden("games_digest.json")
+    games = np.array([g[:3] for g in G["games"]], np.int64)
+    n, T = len(games), int(games[:, 2].max())
+    seeds = G["seed0"] + np.arange(n, dtype=np.int64)
+    env = VecEnv(n, shuffle="mt19937", autoreset=False)
+    _, info = env.reset(seeds=torch.from_numpy(seeds))
+    dev = env.device
+    x = torch.from_numpy(D.lcg_seed(seeds).astype(np.int64)).to(dev)
+    mask = info["action_mask"]
+    active = torch.ones(n, dtype=torch.bool, device=dev)
+    steps = torch.zeros(n, dtype=torch.int64, device=dev)
+    recs = torch.zeros((T, n, D.REC), dtype=torch.uint8, device=dev)
+    for t in range(T):
+        x = (1664525 * x + 1013904223) % (1 << 32)
+        cnt = mask.sum(1, dtype=torch.int64)
+        k = (x >> 16) % cnt.clamp(min=1)
+        a = (mask.to(torch.int64).cumsum(1) > k[:, None]).to(torch.uint8).argmax(1).to(torch.int32)
+        a[cnt == 0] = 0
+        obs, rew, term, trunc, info = env.step(a, active=active)
+        mask = info["action_mask"]
+        r = recs[t]
+        r[:, :297] = obs.to(torch.uint8)
+        r[:, 297:342] = mask.view(torch.uint8)
+        r[:, 342:346] = rew.view(torch.uint8).view(n, 4)
+        r[:, 346] = term.to(torch.uint8)
+        r[:, 347] = info["info_bits"]
+        steps += active
+        active = active & ~term.bool()
+    assert not bool(active.any())
+    assert int(env.obs.max()) < 256
+    rows = _np(env.export_state())
+    st = _np(steps)
+    assert np.array_equal(st, games[:, 2]) and np.array_equal(rows[:, 72], games[:, 0]) and np.array_equal(rows[:, 74], games[:, 1])
+    shas = D.game_shas(_np(recs), st)
+    bad = [i for i in range(n) if shas[i] != G["games"][i][3]]
+    assert not bad, f"{len(bad)} of {n} game digests differ from the reference, first: seed {G['seed0'] + bad[0]}"
+
+
+def test_rollout_without_observations_matches_oracle(VecEnv, oracle):
+    """BASELINE configs[3] (mask + step only): write_obs=False on the single-step path and obs=None on the rollout
+    kernel produce the same masks, rewards, terminations, info bits, actions and states as the oracle."""
+    n, T = 4096 + 17, 48
+    env = VecEnv(n, seed=77, shuffle="mt19937", autoreset=True, prefetch_deals=8)
+    ref = oracle.OracleVec(n, seed_base=77)
+    env.reset()
+    ref.reset()
+    dev = env.device
+    actions = env.sample_random_actions().clone()
+    for t in range(20):  # one launch per lock-step, no observation
+        a = _np(actions).copy()
+        obs, rew, term, trunc, info = env.step(actions, sample_next=True, write_obs=False)
+        robs, rrew, rterm, rinfo, rmask = ref.step(a, autoreset=True)
+        assert np.array_equal(_np(info["action_mask"]), rmask), f"step {t}: mask"
+        assert np.array_equal(_np(rew), rrew) and np.array_equal(_np(term).astype(np.uint8), rterm) and np.array_equal(_np(info["info_bits"]), rinfo)
+        actions = env.next_action.clone()
+    assert np.array_equal(_np(env.export_state()), ref.export_rows())
+    mask = torch.zeros((T, n, 45), dtype=torch.int8, device=dev)
+    rew = torch.zeros((T, n), dtype=torch.float32, device=dev)
+    term = torch.zeros((T, n), dtype=torch.uint8, device=dev)
+    info_b = torch.zeros((T, n), dtype=torch.uint8, device=dev)
+    nxt = torch.zeros((T + 1, n), dtype=torch.int32, device=dev)
+    env.rollout_random(T, actions, obs=None, mask=mask, reward=rew, terminated=term, next_actions=nxt, info=info_b)
+    a = _np(actions)
+    for t in range(T):
+        robs, rrew, rterm, rinfo, rmask = ref.step(a, autoreset=True)
+        assert np.array_equal(_np(mask[t]), rmask), f"rollout step {t}: mask"
+        assert np.array_equal(_np(rew[t]), rrew) and np.array_equal(_np(term[t]), rterm) and np.array_equal(_np(info_b[t]), rinfo)
+        a = _np(nxt[t + 1])
+    assert np.array_equal(_np(env.export_state()), ref.export_rows())
+    assert int(env.stats[0]) > 0

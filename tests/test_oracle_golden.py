@@ -150,3 +150,34 @@ def test_vec_lockstep_autoreset_matches_single(oracle):
             rows[i] = row
     assert v.episodes().tolist() == ep and sum(ep) > 0
     assert v.stats()[0] == sum(ep)
+
+
+def test_ten_thousand_reference_games_by_digest(oracle):
+    """tests/golden/games_digest.json: 10,000 games (773,764 env-steps) played by the UNMODIFIED reference under the LCG
+    policy, one sha256 per game over every step's observation, mask, reward, terminated flag and info bits.  The oracle
+    replays them all in lock-step and must reproduce every digest, move count and winner."""
+    import digest_util as D
+
+    G = load_golden("games_digest.json")
+    games = np.array([g[:3] for g in G["games"]], np.int64)
+    n, T = len(games), int(games[:, 2].max())
+    seeds = G["seed0"] + np.arange(n, dtype=np.uint64)
+    v = oracle.OracleVec(n)
+    _, mask = v.reset(seeds=seeds)
+    x = D.lcg_seed(seeds)
+    steps = np.zeros(n, np.int64)
+    active = np.ones(n, bool)
+    recs = np.zeros((T, n, D.REC), np.uint8)
+    for t in range(T):
+        x = D.lcg_next(x)
+        a = D.lcg_pick(x, mask)
+        obs, rew, term, info, mask = v.step(a, active=active.astype(np.uint8), autoreset=False)
+        recs[t] = D.step_records(obs, mask, rew, term, info)
+        steps += active
+        active &= term == 0
+    assert not active.any()
+    rows = v.export_rows()
+    assert np.array_equal(steps, games[:, 2]) and np.array_equal(rows[:, 72], games[:, 0]) and np.array_equal(rows[:, 74], games[:, 1])
+    shas = D.game_shas(recs, steps)
+    bad = [i for i in range(n) if shas[i] != G["games"][i][3]]
+    assert not bad, f"{len(bad)} of {n} game digests differ, first: seed {G['seed0'] + bad[0]}"
