@@ -115,6 +115,13 @@ typedef struct spl_envs {
 	                        refills the spares in batches; spl_rollout_random (one launch for many lock-steps) takes up to S
 	                        per env and refills behind the launch -- a game lasts >= 17 moves, so S = 8 covers 128 lock-steps
 	                        (an env that runs out is dealt in place, slowly).  Zero it once. */
+	const uint64_t *episode_seeds; /* nullable, SPL_SHUFFLE_MT19937: DEVICE [n][episode_seed_count] engine seeds of every env's
+	                        episodes 1 .. episode_seed_count (episode 0 = the one spl_reset started).  Replay of a reference run:
+	                        the reference's SplendorEnv draws a fresh engine seed from its own PCG64 stream on every reset
+	                        (envs/splendor_env.py:42-43, re-drawn per auto-reset by the vector env, ppo_splendor.py:246-247); with
+	                        this table the auto-resets deal exactly those decks.  Later episodes fall back to the schedule. */
+	int32_t episode_seed_count;
+	int32_t reserved_;
 } spl_envs_t;
 
 /* spl_step_io.flags */
@@ -180,6 +187,16 @@ int spl_rollout_random(const spl_envs_t *envs, const spl_step_io_t *io, int32_t 
  * published flag-last and taken flag-first); otherwise order it with them (same stream, or an event).  An env that finds
  * its ring empty is dealt in place by the step kernel, bit-identically but slowly (one lane's random.Random(seed), ~35 us). */
 int spl_refill_spares(const spl_envs_t *envs, void *stream);
+
+/* Replay of caller-supplied deck permutations (north_star: "a replay mode accepts the reference's deck permutations").
+ * deals: [n][count][SPL_DECK_STRIDE] bytes, HOST or DEVICE memory; deals[e][k] is the deal of env e's (current episode + 1
+ * + k)-th episode, count <= spare_slots.  A deal row is what initial_state() shuffles (engine/state.py:181-211):
+ *   bytes 0..39 the tier-1 card ids in list order (the LAST four are dealt to board slots 0..3: byte 39 -> slot 0, ...,
+ *   byte 36 -> slot 3; deck.pop() continues from byte 35 downwards), 40..69 tier 2, 70..89 tier 3, 90..92 the three visible
+ *   noble indices; 93..95 are ignored.  Rows are validated (each tier a permutation of its own cards, nobles distinct);
+ * returns SPL_E_BADROW if any is not, having loaded none.  The rows go into the ring of prefetched deals (envs->spare):
+ * the next `count` auto-resets of every env use them; refills afterwards follow episode_seeds / the seed schedule. */
+int spl_load_deals(const spl_envs_t *envs, const uint8_t *deals, int32_t count, void *stream);
 
 /* How spl_rollout_random would run `steps` lock-steps of n envs on the current device (measurement aid):
  * out[0] warps per CTA, [1] CTAs, [2] lock-steps per work unit, [3] work units per tile group, [4] CTA barrier per

@@ -18,6 +18,7 @@ Files written:
   bots.json           (obs, mask) states + the decisions of the scripted opponents of scripts/eval_suite.py
   games_digest.json   10,000 reference games under the LCG policy: moves, winner and ONE sha256 per game over every step's
                       (observation, mask, reward, terminated, info bits)  [python oracle/gen_golden.py games_digest: ~1 min on 8 cores]
+  autoreset_stream.json  reference envs auto-reset four times from reset(seed=s): engine seeds, episode start rows, digests
   wrappers.json       SelfPlayWrapper / DualStepNativeWrapper / DualStepSelfPlayWrapper turns (incl. turn-limit draws):
                       rewards, done flags, opponent moves, observation digests per wrapper step
 """
@@ -548,8 +549,46 @@ def gen_wrappers():
     dump("wrappers.json", out)
 
 
+# ----------------------------------------------------------------------------- autoreset_stream.json
+def gen_autoreset_stream():
+    """A reference SplendorEnv that is reset(seed=s) once and then auto-reset four times the way the vector env does it
+    (env.reset() without a seed: the next draw of the env's own PCG64 stream, envs/splendor_env.py:42-43,
+    ppo_splendor.py:246-247).  Engine seeds drawn, start row of every episode, actions, per-step digests in the
+    same-step auto-reset convention (terminal step: reward / terminated of the finished game, observation / mask / row of
+    the new one, info bit 128)."""
+    out = []
+    for s in (0, 1, 7, 42, 2024, 31337, 99991, 123456789):
+        env = ENV.SplendorEnv()
+        twin = np.random.Generator(np.random.PCG64(np.random.SeedSequence(s)))  # gymnasium.utils.seeding.np_random(s)
+        obs, info = env.reset(seed=s)
+        engine_seeds = [int(twin.integers(0, 2**31 - 1))]
+        starts = [pyref.state_to_row(env.state).tolist()]
+        assert starts[0] == pyref.state_to_row(R.initial_state(seed=engine_seeds[0])).tolist()
+        mask = info["action_mask"]
+        x = (s * 2654435761 + 12345) % 2**32
+        actions, digests = [], []
+        while len(starts) < 5:
+            legal = np.flatnonzero(mask)
+            x = (1664525 * x + 1013904223) % 2**32
+            a = int(legal[(x >> 16) % len(legal)]) if len(legal) else 0
+            obs, r, term, trunc, info = env.step(a)
+            bits = info_bits(info, env.state)
+            mask = info["action_mask"]
+            if term:
+                obs, rinfo = env.reset()
+                mask = rinfo["action_mask"]
+                bits |= 128
+                engine_seeds.append(int(twin.integers(0, 2**31 - 1)))
+                starts.append(pyref.state_to_row(env.state).tolist())
+                assert starts[-1] == pyref.state_to_row(R.initial_state(seed=engine_seeds[-1])).tolist()
+            actions.append(a)
+            digests.append(digest(obs, mask, pyref.state_to_row(env.state), r, term, bits))
+        out.append({"seed": s, "engine_seeds": engine_seeds, "starts": starts, "actions": actions, "digests": digests})
+    dump("autoreset_stream.json", out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["mt", "token_return", "initial", "env_seeding", "games", "edges", "bots", "games_digest", "wrappers"]
+    which = sys.argv[1:] or ["mt", "token_return", "initial", "env_seeding", "games", "edges", "bots", "games_digest", "wrappers", "autoreset_stream"]
     for name in which:
         globals()["gen_" + name]()

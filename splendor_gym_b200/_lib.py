@@ -40,7 +40,7 @@ EXPORTS = (
     "spl_dual_combine", "spl_error_string", "spl_version", "spl_host_ret_table", "spl_launch_count",
     "spl_timing_enable", "spl_timing_read", "spl_rollout_random", "spl_scripted_action", "spl_masked_sample", "spl_gae",
     "spl_host_create", "spl_host_destroy", "spl_host_step", "spl_host_observe", "spl_host_set_threads", "spl_host_expand", "spl_rollout_plan", "spl_observe_policy", "spl_masked_sample_f16",
-    "spl_refill_spares", "spl_host_set_pinning", "spl_host_alloc", "spl_host_free", "spl_host_get_stats", "spl_host_store_rate",
+    "spl_refill_spares", "spl_host_set_pinning", "spl_host_alloc", "spl_host_free", "spl_host_get_stats", "spl_host_store_rate", "spl_load_deals",
 )
 
 BOT_RANDOM, BOT_GREEDY_V1, BOT_BASIC_PRIORITY, BOT_GREEDY_V2 = 0, 1, 2, 3
@@ -53,6 +53,7 @@ class SplEnvs(C.Structure):
         ("state", C.c_void_p), ("decks", C.c_void_p), ("episode", C.c_void_p), ("scratch", C.c_void_p),
         ("stride", C.c_int64), ("n", C.c_int64), ("env_offset", C.c_uint64), ("seed_base", C.c_uint64),
         ("shuffle_mode", C.c_int32), ("spare_slots", C.c_int32), ("spare", C.c_void_p),
+        ("episode_seeds", C.c_void_p), ("episode_seed_count", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -146,6 +147,8 @@ def load():
     L.spl_host_observe.argtypes = [vp, C.POINTER(SplEnvs), C.POINTER(SplHostIO), vp]
     L.spl_refill_spares.restype = C.c_int
     L.spl_refill_spares.argtypes = [C.POINTER(SplEnvs), vp]
+    L.spl_load_deals.restype = C.c_int
+    L.spl_load_deals.argtypes = [C.POINTER(SplEnvs), vp, C.c_int32, vp]
     L.spl_rollout_plan.restype = C.c_int
     L.spl_rollout_plan.argtypes = [i64, C.c_int32, C.POINTER(C.c_int32)]
     L.spl_host_expand.restype = C.c_int

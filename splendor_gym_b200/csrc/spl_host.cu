@@ -271,7 +271,8 @@ int spl_host_create(int64_t n, int32_t chunks, spl_host_t** out) {
 	cudaError_t e = cudaGetDevice(&h->device);
 	if (e == cudaSuccess) e = cudaMalloc(&h->d_obs, (size_t)n * SPL_OBS_DIM_ + 64);
 	if (e == cudaSuccess) e = cudaMalloc(&h->d_side, (size_t)n * 16);
-	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_obs, (size_t)n * SPL_OBS_DIM_ + 64, fl);
+	// staging: one full-size slot per group (the nibble form of a partial last group still keeps its wide bytes at +9,504)
+	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_obs, (size_t)h->groups * SPL_GROUP_OBS_BYTES + 64, fl);
 	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_side, (size_t)n * 16, fl);
 	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_act, (size_t)n * 4, fl);
 	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_flags, (size_t)h->groups * 4 + 64, fl);

@@ -287,6 +287,15 @@ __device__ __forceinline__ void spl_state_from_deal(SplState& s, const uint32_t 
 #define SPL_RESET_SPARE 3    /* MT19937 with prefetched deals of the NEXT episode(s) per env (spl_envs_t.spare): take it right here */
 #define SPL_RESET_SPARE_INLINE 4 /* the same inside the rollout kernel: a missing spare is dealt in place by one lane (slow, rare) */
 
+// Engine seed of (env, episode) under SPL_SHUFFLE_MT19937: the library's own schedule, or -- replay of a reference
+// run -- the caller's table of the seeds its SplendorEnv instances drew from their PCG64 streams on every auto-reset
+// (envs/splendor_env.py:42-43; spl_envs_t.episode_seeds).  Episode 0 is the one spl_reset started (its seeds argument).
+__device__ __forceinline__ uint64_t spl_episode_seed(uint64_t seed_base, uint64_t env_offset, int64_t env, uint32_t ep,
+                                                      const uint64_t* table, int table_eps) {
+	if (table != nullptr && ep >= 1u && ep <= (uint32_t)table_eps) return table[env * table_eps + (int64_t)(ep - 1u)];
+	return (seed_base + 1000003ull * ep + env_offset + (uint64_t)env) % 2147483647ull;
+}
+
 struct StepParams {
 	uint4* state;
 	int64_t stride;
@@ -295,6 +304,8 @@ struct StepParams {
 	int32_t* scratch;
 	int64_t n;
 	uint64_t env_offset, seed_base;
+	const uint64_t* ep_seeds;  // spl_envs_t.episode_seeds [n][ep_seed_count] or nullptr
+	int ep_seed_count;
 	const int32_t* actions;
 	const uint8_t* active;
 	int32_t* obs;
@@ -423,7 +434,7 @@ __device__ __forceinline__ void spl_tile_step(const StepParams& p, const SplTile
 				if (lane == src) {
 					const uint32_t ep = __ldcg(p.episode + env) + 1u;
 					p.episode[env] = ep;
-					spl_mt_deal_in_place((p.seed_base + 1000003ull * ep + p.env_offset + (uint64_t)env) % 2147483647ull, tl.smem,
+					spl_mt_deal_in_place(spl_episode_seed(p.seed_base, p.env_offset, env, ep, p.ep_seeds, p.ep_seed_count), tl.smem,
 					                     p.decks + env * SPL_DECK_STRIDE);
 					uint32_t board[3] = {tl.smem[648], tl.smem[649], tl.smem[650]};
 					spl_state_from_deal(s, board, tl.smem[651]);
@@ -723,6 +734,8 @@ struct ResetParams {
 	const int32_t* list;  // list[0] = count, list[4..] = env indices; nullptr => all envs 0..n-1
 	int64_t n;
 	uint64_t env_offset, seed_base;
+	const uint64_t* ep_seeds;  // spl_envs_t.episode_seeds [n][ep_seed_count] or nullptr
+	int ep_seed_count;
 	const uint64_t* seeds;  // explicit engine seeds [n] or nullptr
 	int32_t* obs;
 	int8_t* mask;
@@ -908,7 +921,8 @@ __global__ void __launch_bounds__(32) spl_reset_kernel(const ResetParams p) {
 				p.episode[env] = ep;
 			}
 			uint64_t genv = p.env_offset + (uint64_t)env;
-			seed = (p.seeds && !spare_mode) ? p.seeds[env] : (p.seed_base + 1000003ull * ep + genv) % 2147483647ull;
+			seed = (p.seeds && !spare_mode) ? p.seeds[env] : spl_episode_seed(p.seed_base, p.env_offset, env, ep, p.ep_seeds, p.ep_seed_count);
+			(void)genv;
 		}
 		spl_fresh_state(s);
 		if (SHUFFLE == SPL_SHUFFLE_MT19937) {
@@ -1058,7 +1072,9 @@ __global__ void __launch_bounds__(SPL_DEAL_THREADS) spl_spare_deal_kernel(const 
 		// the first episode AFTER the current one that lives in this slot; the counter itself moves when a spare is taken
 		const uint32_t cur = p.episode[env];
 		const uint32_t ep = cur + 1u + (uint32_t)(((uint32_t)slot + (uint32_t)R - (cur + 1u) % (uint32_t)R) % (uint32_t)R);
-		const uint32_t key = (uint32_t)((p.seed_base + 1000003ull * ep + p.env_offset + (uint64_t)env) % 2147483647ull);  // one-word key
+		const uint64_t key64 = spl_episode_seed(p.seed_base, p.env_offset, env, ep, p.ep_seeds, p.ep_seed_count);
+		if (key64 >> 32) continue;  // a table seed wider than one word: left to the consumer's in-place deal (full init_by_array)
+		const uint32_t key = (uint32_t)key64;  // one-word key
 		const bool overflow = !spl_mt_deal_stream(key, G, deck, (uint32_t)p.max_outputs);
 		if (overflow) continue;
 		// bytes 90..92: the three visible nobles (already there), 93..94: episode tag, 95: ready
@@ -1146,6 +1162,39 @@ __global__ void spl_import_kernel(uint4* state, int64_t stride, uint8_t* decks, 
 		state[pl * stride + env] = make_uint4(w[4 * pl + 0], w[4 * pl + 1], w[4 * pl + 2], w[4 * pl + 3]);
 }
 
+// spl_load_deals: caller-supplied deals -> ring slots.  One thread per (env, k); validation first (all rows), then the copy.
+__global__ void spl_check_deals_kernel(const uint8_t* __restrict__ deals, int64_t items, int* bad) {
+	const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (it >= items) return;
+	const uint8_t* d = deals + it * SPL_DECK_STRIDE;
+	const int lo[4] = {0, 40, 70, 90};
+	bool ok = true;
+	for (int t = 0; t < 3; t++) {  // each tier: a permutation of its own card ids
+		uint64_t seen = 0;
+		for (int k = lo[t]; k < lo[t + 1]; k++) {
+			const int id = (int)d[k] - lo[t];
+			ok = ok && id >= 0 && id < lo[t + 1] - lo[t];
+			if (ok) seen |= 1ull << id;
+		}
+		ok = ok && seen == ((1ull << (lo[t + 1] - lo[t])) - 1ull);
+	}
+	ok = ok && d[90] < 10 && d[91] < 10 && d[92] < 10 && d[90] != d[91] && d[90] != d[92] && d[91] != d[92];
+	if (!ok) atomicAdd(bad, 1);
+}
+
+__global__ void spl_load_deals_kernel(const uint8_t* __restrict__ deals, int64_t n, int count, const uint32_t* __restrict__ episode,
+                                      uint8_t* spare, int slots, const int* bad) {
+	const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (it >= n * count || *bad != 0) return;
+	const int64_t env = it / count;
+	const uint32_t ep = episode[env] + 1u + (uint32_t)(it - env * count);
+	const uint32_t* src = reinterpret_cast<const uint32_t*>(deals + it * SPL_DECK_STRIDE);
+	uint32_t* dst = reinterpret_cast<uint32_t*>(spare + (env * slots + (int64_t)(ep % (uint32_t)slots)) * SPL_DECK_STRIDE);
+	for (int k = 0; k < 23; k++) dst[k] = src[k];
+	__threadfence();  // tag + ready flag last, as every other writer of the ring does
+	dst[23] = (src[23] & 0xFFu) | ((ep & 0xFFFFu) << 8) | 0x01000000u;
+}
+
 // final_rewards[player] (envs/splendor_env.py:92-115) from an info byte; 0 when absent
 __device__ __forceinline__ float spl_final_reward(uint32_t info, uint32_t player) {
 	if (!(info & SPL_INFO_TERMINATED) || (info & (SPL_INFO_NOLEGAL_DRAW | SPL_INFO_ERROR))) return 0.0f;
@@ -1216,7 +1265,7 @@ static inline int knob(int k, int dflt) { return g_knob_set[k] ? g_knobs[k] : df
 
 extern "C" {
 
-int spl_version(void) { return 110; }  // 110: spl_envs.spare_slots, spl_step_io.flags, spl_refill_spares
+int spl_version(void) { return 120; }  // 120: spl_envs.episode_seeds, spl_load_deals, spl_host_alloc / push path, SPL_E_BADROW
 
 int spl_timing_enable(int on) {
 	if (on && !g_ev_created) {
@@ -1347,6 +1396,7 @@ static int launch_reset(const spl_envs_t* e, const int32_t* list, const uint64_t
 	p.action_t_base = io ? io->action_t_base : nullptr;
 	p.state = (uint4*)e->state, p.stride = e->stride, p.decks = e->decks, p.episode = e->episode, p.list = list;
 	p.n = e->n, p.env_offset = e->env_offset, p.seed_base = e->seed_base, p.seeds = seeds, p.obs = obs, p.mask = mask;
+	p.ep_seeds = e->episode_seeds, p.ep_seed_count = e->episode_seeds ? e->episode_seed_count : 0;
 	p.bump_episode = bump;
 	p.spare_out = nullptr, p.refill = nullptr;
 	p.spare_slots = 1, p.list_is_envs = 0, p.max_outputs = knob(K_DEAL_MAX_OUTPUTS, 227);
@@ -1408,6 +1458,7 @@ int spl_reset(const spl_envs_t* envs, const uint64_t* seeds, const uint8_t* rese
 static void fill_step_params(StepParams& p, const spl_envs_t* e, const spl_step_io_t* io, int32_t* obs, int8_t* mask) {
 	p.state = (uint4*)e->state, p.stride = e->stride, p.decks = e->decks, p.episode = e->episode, p.scratch = e->scratch;
 	p.n = e->n, p.env_offset = e->env_offset, p.seed_base = e->seed_base;
+	p.ep_seeds = e->episode_seeds, p.ep_seed_count = e->episode_seeds ? e->episode_seed_count : 0;
 	p.actions = io ? io->actions : nullptr, p.active = io ? io->active : nullptr;
 	p.obs = obs, p.mask = mask;
 	p.reward = io ? io->reward : nullptr, p.terminated = io ? io->terminated : nullptr, p.info = io ? io->info : nullptr;
@@ -1667,6 +1718,38 @@ int spl_import_state(const spl_envs_t* envs, const int32_t* rows, const uint8_t*
 	SPL_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
 	SPL_CUDA(cudaFreeAsync(bad, (cudaStream_t)stream));
 	SPL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+	return nbad ? SPL_E_BADROW : 0;
+}
+
+int spl_load_deals(const spl_envs_t* envs, const uint8_t* deals, int32_t count, void* stream) {
+	int rc = check_envs(envs);
+	if (rc) return rc;
+	if (!deals || count <= 0 || envs->shuffle_mode != SPL_SHUFFLE_MT19937 || envs->spare == nullptr || count > spare_slots(envs)) return SPL_E_BADARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int64_t items = envs->n * count;
+	const size_t bytes = (size_t)items * SPL_DECK_STRIDE;
+	cudaPointerAttributes at;
+	const bool on_device = cudaPointerGetAttributes(&at, deals) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+	cudaGetLastError();
+	uint8_t* staged = nullptr;
+	if (!on_device) {
+		SPL_CUDA(cudaMallocAsync(&staged, bytes, st));
+		SPL_CUDA(cudaMemcpyAsync(staged, deals, bytes, cudaMemcpyHostToDevice, st));
+		deals = staged;
+	}
+	int* bad = nullptr;
+	SPL_CUDA(cudaMallocAsync(&bad, sizeof(int), st));
+	SPL_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+	const unsigned grid = (unsigned)((items + 127) / 128);
+	spl_check_deals_kernel<<<grid, 128, 0, st>>>(deals, items, bad);
+	spl_load_deals_kernel<<<grid, 128, 0, st>>>(deals, envs->n, count, envs->episode, envs->spare, spare_slots(envs), bad);
+	g_launches += 2;
+	SPL_CUDA(cudaGetLastError());
+	int nbad = 0;
+	SPL_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+	SPL_CUDA(cudaFreeAsync(bad, st));
+	if (staged) SPL_CUDA(cudaFreeAsync(staged, st));
+	SPL_CUDA(cudaStreamSynchronize(st));
 	return nbad ? SPL_E_BADROW : 0;
 }
 

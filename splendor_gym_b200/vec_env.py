@@ -479,6 +479,51 @@ class SplendorVecEnv:
             L.check(self.lib.spl_import_state(C.byref(self._envs), rows.data_ptr(), _ptr(which), self._stream()), "spl_import_state")
         self._is_reset = True
 
+    # ------------------------------------------------------------------ replay of a reference run's decks
+    def set_episode_seeds(self, table: Optional[torch.Tensor]) -> None:
+        """Engine seeds of every env's episodes 1..E (``[N, E]`` integers; ``None`` = back to the library's schedule), for
+        ``shuffle="mt19937"``.  The reference's ``SplendorEnv`` draws a fresh engine seed from its own PCG64 stream on every
+        reset (envs/splendor_env.py:42-43; the vector env re-draws on each auto-reset, ppo_splendor.py:246-247): pass those
+        draws here and ``reset(seeds=first_draws)``, and every auto-reset deals exactly the reference's decks.
+        Call it BEFORE ``reset`` (which fills the ring of prefetched deals from it)."""
+        if table is None:
+            self._episode_seeds = None
+            self._envs.episode_seeds, self._envs.episode_seed_count = None, 0
+            return
+        if self.shuffle_mode != L.SHUFFLE_MT19937:
+            raise L.SplendorB200Error("set_episode_seeds needs shuffle='mt19937' (the reference's random.Random decks)")
+        t = torch.as_tensor(table).to(device=self.device, dtype=torch.int64).contiguous()
+        if t.dim() != 2 or t.shape[0] != self.n or t.shape[1] < 1:
+            raise ValueError("episode seeds must be [N, E]")
+        self._episode_seeds = t  # (kept alive: the struct holds its address)
+        self._envs.episode_seeds, self._envs.episode_seed_count = t.data_ptr(), int(t.shape[1])
+
+    def load_deals(self, deals) -> None:
+        """Caller-supplied deck permutations for every env's next ``k`` episodes (``spl_load_deals``): ``deals`` is
+        ``uint8 [N, k, 96]`` (host or device), ``k <= prefetch_deals``; row format in include/splendor_b200.h, or
+        ``deals_from_rows(rows)`` from exported initial-state rows (e.g. of a reference run)."""
+        if self.spare is None:
+            raise L.SplendorB200Error("load_deals needs shuffle='mt19937' with prefetch_deals")
+        d = torch.as_tensor(deals)
+        if d.dtype != torch.uint8 or d.dim() != 3 or d.shape[0] != self.n or d.shape[2] != L.DECK_STRIDE:
+            raise ValueError("deals must be uint8 [N, k, 96]")
+        d = d.contiguous()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.spl_load_deals(C.byref(self._envs), d.data_ptr(), int(d.shape[1]), self._stream()), "spl_load_deals")
+
+    @staticmethod
+    def deals_from_rows(rows: torch.Tensor) -> torch.Tensor:
+        """Flat rows of INITIAL states (``export_state`` layout, as ``initial_state`` leaves them: 36 / 26 / 16 cards in the
+        decks, 12 on the board) -> ``uint8 [N, 96]`` deal rows: the shuffled tier lists with the four board cards put back
+        at the end in dealing order (engine/state.py:190-191) and the three visible nobles."""
+        r = torch.as_tensor(rows).to(torch.int64)
+        out = torch.full((r.shape[0], L.DECK_STRIDE), 255, dtype=torch.int64, device=r.device)
+        for first, size, deck_col, board_col in ((0, 40, 76, 52), (40, 30, 116, 56), (70, 20, 146, 60)):
+            out[:, first:first + size - 4] = r[:, deck_col:deck_col + size - 4]
+            out[:, first + size - 4:first + size] = r[:, board_col:board_col + 4].flip(1)
+        out[:, 90:93] = r[:, 67:70]
+        return out.to(torch.uint8)
+
     # ------------------------------------------------------------------ dual step (self-play turn)
     def dual_step(self, agent_actions: torch.Tensor, opponent_policy: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
                   reward_mode: str = "native"):

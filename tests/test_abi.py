@@ -42,8 +42,9 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layouts_match_header():
     from splendor_gym_b200 import _lib
 
-    # struct spl_envs: 4 pointers, 2 int64, 2 uint64, 2 int32, 1 pointer ; struct spl_step_io: 9 pointers, 2 uint64, 1 pointer, 2 int32
-    assert C.sizeof(_lib.SplEnvs) == 4 * 8 + 4 * 8 + 8 + 8 and _lib.SplEnvs.spare.offset == 72
+    # struct spl_envs: 4 pointers, 2 int64, 2 uint64, 2 int32, 2 pointers, 2 int32 ; struct spl_step_io: 9 pointers, 2 uint64, 1 pointer, 2 int32
+    assert C.sizeof(_lib.SplEnvs) == 4 * 8 + 4 * 8 + 8 + 2 * 8 + 8 and _lib.SplEnvs.spare.offset == 72
+    assert _lib.SplEnvs.episode_seeds.offset == 80 and _lib.SplEnvs.episode_seed_count.offset == 88
     assert C.sizeof(_lib.SplStepIO) == 9 * 8 + 2 * 8 + 8 + 8 + 2 * 8 and _lib.SplStepIO.obs_f16.offset == 104
     assert _lib.SplEnvs.shuffle_mode.offset == 64 and _lib.SplStepIO.autoreset.offset == 96
     # struct spl_host_io: 9 pointers, 2 uint64, 2 int32
@@ -60,7 +61,7 @@ def test_struct_layouts_match_header():
 
 
 def test_host_only_entry_points(lib):
-    assert lib.spl_version() >= 100
+    assert lib.spl_version() >= 120
     assert lib.spl_error_string(0) == b"ok" and b"bad argument" in lib.spl_error_string(-1)
     assert lib.spl_launch_count() == 0  # nothing has been launched by loading the library
     t = np.zeros(8910, np.uint64)

@@ -749,3 +749,38 @@ def test_rollout_without_observations_matches_oracle(VecEnv, oracle):
         a = _np(nxt[t + 1])
     assert np.array_equal(_np(env.export_state()), ref.export_rows())
     assert int(env.stats[0]) > 0
+
+
+@pytest.mark.parametrize("how", ["seed_table", "seed_table_ring1", "seed_table_no_ring", "load_deals"])
+def test_replay_of_reference_autoreset_stream(VecEnv, how):
+    """Replay mode (north_star: "accepts the reference's deck permutations").  tests/golden/autoreset_stream.json holds
+    reference SplendorEnv instances that were reset(seed=s) and then auto-reset four times, each time drawing a new engine
+    seed from their own PCG64 stream.  Fed with those draws (set_episode_seeds) or with the dealt decks themselves
+    (load_deals), the batched path reproduces every env step by step across all the auto-resets."""
+    from test_oracle_golden import digest
+
+    G = load_golden("autoreset_stream.json")
+    n = len(G)
+    prefetch = {"seed_table": 4, "seed_table_ring1": 1, "seed_table_no_ring": False, "load_deals": 4}[how]
+    env = VecEnv(n, shuffle="mt19937", autoreset=True, prefetch_deals=prefetch, seed=555)
+    if how != "load_deals":
+        env.set_episode_seeds(torch.tensor([g["engine_seeds"][1:] for g in G], dtype=torch.int64))
+    env.reset(seeds=torch.tensor([g["engine_seeds"][0] for g in G], dtype=torch.int64))
+    if how == "load_deals":
+        starts = torch.tensor([g["starts"][1:] for g in G], dtype=torch.int32)  # [n, 4, 166]
+        env.load_deals(torch.stack([VecEnv.deals_from_rows(starts[:, k]) for k in range(4)], dim=1))
+        with pytest.raises(Exception, match="outside the engine's domain"):
+            bad = torch.zeros((n, 1, 96), dtype=torch.uint8)
+            env.load_deals(bad)
+    assert np.array_equal(_np(env.export_state()), np.array([g["starts"][0] for g in G], np.int32))
+    T = max(len(g["actions"]) for g in G)
+    for t in range(T):
+        live = np.array([t < len(g["actions"]) for g in G])
+        a = np.array([g["actions"][t] if live[i] else 0 for i, g in enumerate(G)], np.int32)
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(a).cuda(), active=torch.from_numpy(live).cuda())
+        rows = _np(env.export_state())
+        o, m, r, te, ib = _np(obs), _np(info["action_mask"]), _np(rew), _np(term), _np(info["info_bits"])
+        for i, g in enumerate(G):
+            if live[i]:
+                assert digest(o[i], m[i], rows[i], r[i], te[i], int(ib[i])) == g["digests"][t], (how, g["seed"], t)
+    assert _np(env.episode).tolist() == [4] * n
