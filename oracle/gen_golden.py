@@ -19,6 +19,7 @@ Files written:
   games_digest.json   10,000 reference games under the LCG policy: moves, winner and ONE sha256 per game over every step's
                       (observation, mask, reward, terminated, info bits)  [python oracle/gen_golden.py games_digest: ~1 min on 8 cores]
   autoreset_stream.json  reference envs auto-reset four times from reset(seed=s): engine seeds, episode start rows, digests
+  logger_strings.json decode_action strings of scripts/game_logger.py and PlayerState.can_afford results on game positions
   wrappers.json       SelfPlayWrapper / DualStepNativeWrapper / DualStepSelfPlayWrapper turns (incl. turn-limit draws):
                       rewards, done flags, opponent moves, observation digests per wrapper step
 """
@@ -587,8 +588,50 @@ def gen_autoreset_stream():
     dump("autoreset_stream.json", out)
 
 
+# ----------------------------------------------------------------------------- logger_strings.json
+def gen_logger_strings():
+    """scripts/game_logger.py:98-170 (decode_action for all 45 actions) and engine/state.py:61-71 (PlayerState.can_afford for
+    every card on the board / in hand) on positions from a played game, incl. reduced take-3s and empty slots."""
+    sys.path.insert(0, pyref.REFERENCE_ROOT)
+    from splendor_gym.scripts.game_logger import SplendorGameLogger
+
+    lg = SplendorGameLogger()
+    out = []
+    for seed, stops in ((5, (0, 9, 25, 48)), (11, (14, 33, 60))):
+        state = R.initial_state(seed=seed)
+        x = seed
+        t = 0
+        while True:
+            if t in stops:
+                s = state
+                if t == 25:  # reduced take-3 (two colours left) and an empty board slot
+                    import copy
+
+                    s = copy.deepcopy(state)
+                    s.bank[0] = s.bank[2] = s.bank[4] = 0
+                    s.board[1][2] = None
+                elif t == 33:
+                    import copy
+
+                    s = copy.deepcopy(state)
+                    s.bank[:5] = [0, 0, 0, 2, 0]
+                me = s.players[s.to_play]
+                cards = [c for tier in (1, 2, 3) for c in s.board[tier] if c is not None] + list(me.reserved)
+                out.append({"row": pyref.state_to_row(s).tolist(), "actions": [lg.decode_action(a, s) for a in range(46)],
+                            "can_afford": [[c.id, bool(me.can_afford(c)[0]), list(me.can_afford(c)[1])] for c in cards]})
+            if t >= max(stops) or R.is_terminal(state):
+                break
+            mask = R.legal_moves(state)
+            legal = [i for i, v in enumerate(mask) if v]
+            x = (1664525 * x + 1013904223) % 2**32
+            state = R.apply_action(state, legal[(x >> 16) % len(legal)])
+            t += 1
+    assert len(out) == 7
+    dump("logger_strings.json", out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["mt", "token_return", "initial", "env_seeding", "games", "edges", "bots", "games_digest", "wrappers", "autoreset_stream"]
+    which = sys.argv[1:] or ["mt", "token_return", "initial", "env_seeding", "games", "edges", "bots", "games_digest", "wrappers", "autoreset_stream", "logger_strings"]
     for name in which:
         globals()["gen_" + name]()

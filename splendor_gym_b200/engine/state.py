@@ -68,6 +68,13 @@ class PlayerState:
     revealed_reserved: List[bool] = field(default_factory=list)
     nobles: List[Noble] = field(default_factory=list)
 
+    def can_afford(self, card: Card):
+        """(affordable, per-colour cost after bonuses) -- engine/state.py:61-71.  Kept for API parity (the reference's
+        bots and debugging helpers call it); the step path evaluates affordability on the device (spl_legal_mask)."""
+        owed = [max(0, card.cost.get(c, 0) - self.bonuses[i]) for i, c in enumerate(STANDARD_COLORS)]
+        gold_needed = sum(max(0, o - self.tokens[i]) for i, o in enumerate(owed))
+        return self.tokens[COLOR_INDEX["gold"]] >= gold_needed, owed
+
 
 @dataclass
 class SplendorState:

@@ -26,30 +26,50 @@ from .ppo_rollout import ActorCritic
 
 
 class OpponentPool:
-    """Per-env opponent ids with per-episode resampling (ppo_splendor.py:135-143): id -1 = the current policy (greedy),
-    id k >= 0 = frozen snapshot k.  `act` runs one batched forward per distinct id present (grouped inference)."""
+    """Per-env opponents with per-episode resampling, the batched form of ppo_splendor.py:135-143,366-370:
+
+    * every env holds one opponent for the whole episode; when its episode ends a new one is drawn -- the CURRENT policy
+      with probability ``p_current`` (always, while the pool is empty), else a uniformly random frozen snapshot (:137-143);
+    * ``add_snapshot`` appends a frozen copy of the actor and drops the oldest beyond ``pool_size`` (:366-370).  An env
+      that is still playing against a dropped snapshot keeps it until its episode ends, as the reference's closure does
+      (training_utils.py:263-276 builds the frozen policy once, in ``wrapper.reset()``);
+    * opponents act greedily: argmax of the masked logits (scripts/eval_suite.py:131-141, training_utils.py:270-276).
+
+    Opponent ids: -1 = the current policy, k >= 0 = the k-th snapshot ever taken.  ``act`` runs one batched forward per
+    distinct id present (grouped inference)."""
 
     def __init__(self, net: ActorCritic, n: int, device, p_current: float = 0.25, pool_size: int = 12):
         self.net, self.n, self.device = net, n, device
         self.p_current, self.pool_size = p_current, pool_size
-        self.snapshots: list[nn.Module] = []
+        self.pool: list[int] = []             # ids of the snapshots new episodes can draw, oldest first
+        self.models: dict[int, nn.Module] = {}  # id -> frozen actor (also dropped ones that an env still plays against)
+        self.taken = 0
         self.opp_id = torch.full((n,), -1, dtype=torch.int64, device=device)
+
+    @property
+    def snapshots(self) -> list:
+        return [self.models[k] for k in self.pool]
 
     def add_snapshot(self):
         snap = copy.deepcopy(self.net.actor).eval()
         for p in snap.parameters():
             p.requires_grad_(False)
-        self.snapshots.append(snap)
-        if len(self.snapshots) > self.pool_size:
-            self.snapshots.pop(0)
-            self.opp_id = torch.where(self.opp_id == 0, torch.full_like(self.opp_id, -1), self.opp_id - (self.opp_id > 0).long())
+        self.models[self.taken] = snap
+        self.pool.append(self.taken)
+        self.taken += 1
+        if len(self.pool) > self.pool_size:
+            self.pool.pop(0)
+        in_use = set(self.opp_id.unique().tolist())
+        for k in [k for k in self.models if k not in self.pool and k not in in_use]:
+            del self.models[k]
 
     def resample(self, done: torch.Tensor):
         """New opponent for every env whose episode just ended (the reference resamples in wrapper.reset())."""
-        if not self.snapshots:
+        if not self.pool:
             return
         cur = torch.rand(self.n, device=self.device) < self.p_current
-        pick = torch.randint(0, len(self.snapshots), (self.n,), device=self.device)
+        ids = torch.tensor(self.pool, dtype=torch.int64, device=self.device)
+        pick = ids[torch.randint(0, len(self.pool), (self.n,), device=self.device)]
         new = torch.where(cur, torch.full_like(pick, -1), pick)
         self.opp_id = torch.where(done, new, self.opp_id)
 
@@ -57,12 +77,9 @@ class OpponentPool:
     def act(self, obs: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         x = obs.float()
         logits = torch.empty((self.n, 45), dtype=torch.float32, device=self.device)
-        ids = [-1] + list(range(len(self.snapshots)))
-        for k in ids:
+        for k in self.opp_id.unique().tolist():
             sel = (self.opp_id == k).nonzero(as_tuple=True)[0]
-            if sel.numel() == 0:
-                continue
-            model = self.net.actor if k < 0 else self.snapshots[k]
+            model = self.net.actor if k < 0 else self.models[k]
             logits[sel] = model(x[sel]).float()
         return masked_sample(logits, mask, greedy=True, want_logprob=False)[0]  # model_greedy_policy_from
 

@@ -14,30 +14,41 @@ import torch
 from .engine.encode import TAKE3_COMBOS
 from .vec_env import SplendorVecEnv
 
-_ABBR = "WUGRK"  # white blue green red black
+_ABBR = "wbgrk"  # white blue green red black, the abbreviations of scripts/game_logger.py:53 (gold is "G")
 
 
-def describe_action(action: int, bank=None) -> str:
-    """Human-readable action; with the bank given, a take-3 is shown with the colours it really takes."""
+def _card_text(card) -> str:
+    """``g-1pt-2b3r3k``: colour, points, cost (scripts/game_logger.py:56-69)."""
+    if card is None:
+        return "[empty]"
+    cost = "".join(f"{card.cost[c]}{_ABBR[i]}" for i, c in enumerate(("white", "blue", "green", "red", "black")) if card.cost.get(c, 0) > 0)
+    return f"{card.color[0] if card.color != 'black' else 'k'}-{card.points}pt-{cost or 'free'}"
+
+
+def describe_action(action: int, state) -> str:
+    """The reference game logger's one-line description of ``action`` in ``state`` (scripts/game_logger.py:98-170;
+    pinned string by string in tests/golden/logger_strings.json).  ``state``: a ``SplendorState`` mirror or a flat row."""
+    from .engine.state import SplendorState, row_to_state
+
+    s = state if isinstance(state, SplendorState) else row_to_state(state)
     a = int(action)
     if 0 <= a < 10:
-        combo = TAKE3_COMBOS[a]
-        if bank is not None:
-            avail = [c for c in range(5) if bank[c] >= 1]
-            if len(avail) < 3:
-                return f"Take{len(avail)}: {''.join(_ABBR[c] for c in avail)} (reduced)"
-        return "Take3: " + "".join(_ABBR[c] for c in combo)
-    if a < 15:
+        avail = [c for c in range(5) if s.bank[c] >= 1]
+        if len(avail) >= 3:
+            return "Take3: " + "".join(_ABBR[c] for c in TAKE3_COMBOS[a])
+        if avail:  # the engine hands out what is left (engine/rules.py:45-58)
+            return f"Take{len(avail)}: {''.join(_ABBR[c] for c in avail)} (reduced)"
+    elif a < 15:
         return f"Take2: {_ABBR[a - 10] * 2}"
-    if a < 27:
-        return f"Buy: T{1 + (a - 15) // 4}S{1 + (a - 15) % 4}"
-    if a < 39:
-        return f"Reserve: T{1 + (a - 27) // 4}S{1 + (a - 27) % 4}"
-    if a < 42:
-        return f"Reserve: T{a - 38} deck"
-    if a < 45:
-        return f"Buy reserved #{a - 41}"
-    return f"invalid({a})"
+    elif a < 39:
+        verb, k = ("Buy", a - 15) if a < 27 else ("Reserve", a - 27)
+        return f"{verb}: T{1 + k // 4}S{1 + k % 4} {_card_text(s.board[1 + k // 4][k % 4])}"
+    elif a < 42:
+        return f"Reserve: T{a - 38} blind"
+    elif a < 45:
+        mine = s.players[s.to_play].reserved
+        return f"BuyReserved: #{a - 41} {_card_text(mine[a - 42]) if a - 42 < len(mine) else '[empty]'}"
+    return f"Action{a}"
 
 
 @dataclass

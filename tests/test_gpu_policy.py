@@ -177,5 +177,52 @@ def test_trajectory_log_and_replay():
         o, *_ = twin.step(traj.actions[t])
         assert torch.equal(o, obs[t]), t
     assert int(traj.terminated.sum()) > 1000
-    assert describe_action(0) == "Take3: WUG" and describe_action(12) == "Take2: GG" and describe_action(20) == "Buy: T2S2"
-    assert describe_action(41) == "Reserve: T3 deck" and describe_action(0, bank=[1, 0, 2, 0, 0, 0]) == "Take2: WG (reduced)"
+    assert describe_action(12, env.export_state()[0].cpu().numpy()) == "Take2: gg"  # (every string: test_logger_strings_and_can_afford...)
+
+
+@pytest.mark.gpu
+def test_opponent_pool_follows_the_reference_sampling_rules():
+    """OpponentPool against the rules of ppo_splendor.py:135-143,366-370 and training_utils.py:263-276: current policy while
+    the pool is empty, p_current afterwards, snapshots uniform, resampling only where an episode ended, FIFO pool with a
+    dropped snapshot kept for the envs still playing against it, greedy masked argmax of the env's OWN opponent."""
+    import torch
+    from splendor_gym_b200.scripts.ppo_rollout import ActorCritic
+    from splendor_gym_b200.scripts.ppo_train import OpponentPool
+
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    n = 60000
+    net = ActorCritic().to(dev)
+    pool = OpponentPool(net, n, dev, p_current=0.25, pool_size=3)
+    everyone = torch.ones(n, dtype=torch.bool, device=dev)
+    pool.resample(everyone)
+    assert bool((pool.opp_id == -1).all())  # len(pool) == 0 -> the current policy (:139)
+    for k in range(3):
+        with torch.no_grad():
+            for p in net.actor.parameters():
+                p.add_(0.05 * torch.randn_like(p))  # every snapshot is a different network
+        pool.add_snapshot()
+    pool.resample(everyone)
+    frac = [(pool.opp_id == k).float().mean().item() for k in (-1, 0, 1, 2)]
+    assert abs(frac[0] - 0.25) < 0.01 and all(abs(f - 0.25) < 0.01 for f in frac[1:])  # p_current, then uniform over 3 snapshots
+    before = pool.opp_id.clone()
+    half = torch.arange(n, device=dev) % 2 == 0
+    pool.resample(half)
+    assert torch.equal(pool.opp_id[~half], before[~half]) and not torch.equal(pool.opp_id[half], before[half])
+    # a fourth snapshot drops id 0 from the pool; envs playing against it keep it until their episode ends
+    pool.add_snapshot()
+    assert pool.pool == [1, 2, 3] and 0 in pool.models and bool((pool.opp_id == 0).any())
+    obs = torch.randint(0, 6, (n, 297), device=dev, dtype=torch.int32)
+    mask = (torch.rand(n, 45, device=dev) < 0.3).to(torch.int8)
+    mask[:, 0] = 1
+    act = pool.act(obs, mask)
+    with torch.no_grad():
+        for k in (-1, 0, 1, 2):
+            sel = pool.opp_id == k
+            model = net.actor if k < 0 else pool.models[k]
+            logits = model(obs[sel].float()).masked_fill(mask[sel] < 0.5, float("-inf"))  # training_utils.py:270-276
+            assert torch.equal(act[sel].long(), logits.argmax(dim=-1)), k
+    pool.resample(everyone)
+    assert not bool((pool.opp_id == 0).any())
+    pool.add_snapshot()
+    assert 0 not in pool.models and pool.pool == [2, 3, 4]

@@ -181,3 +181,20 @@ def test_ten_thousand_reference_games_by_digest(oracle):
     shas = D.game_shas(recs, steps)
     bad = [i for i in range(n) if shas[i] != G["games"][i][3]]
     assert not bad, f"{len(bad)} of {n} game digests differ, first: seed {G['seed0'] + bad[0]}"
+
+
+def test_logger_strings_and_can_afford_match_the_reference():
+    """tests/golden/logger_strings.json: decode_action of the reference's scripts/game_logger.py for all 45 actions (+1 out of
+    range) and PlayerState.can_afford for every visible / reserved card, on seven positions incl. reduced take-3s and empty
+    slots.  The host mirror (no device needed) reproduces every string and every (affordable, cost_remaining) pair."""
+    from splendor_gym_b200.engine.state import CARDS, row_to_state
+    from splendor_gym_b200.trajectory import describe_action
+
+    for pos in load_golden("logger_strings.json"):
+        s = row_to_state(np.array(pos["row"], np.int32))
+        assert [describe_action(a, s) for a in range(46)] == pos["actions"]
+        assert describe_action(7, pos["row"]) == pos["actions"][7]
+        me = s.players[s.to_play]
+        for cid, ok, owed in pos["can_afford"]:
+            got_ok, got_owed = me.can_afford(CARDS[cid])
+            assert (bool(got_ok), list(got_owed)) == (ok, owed), cid
