@@ -708,7 +708,7 @@ def run_b200(args):
                "host_written_gbs": written_gbs, "host_store_gbs": store_gbs, "host_fill_gbs": fill_gbs,
                "frac_of_host_ceiling": written_gbs / store_gbs if store_gbs > 0 else None,
                "host_ceiling": "spl_host_store_rate: the worker pool widening uint8 -> int32 with non-temporal stores into %d MB (mode 1; "
-                               "host_fill_gbs = plain streaming fill), best of 5, same threads and pinning as the path, summed over the "
+                               "host_fill_gbs = plain streaming fill), sustained over >= 40 ms, same threads and pinning as the path, summed over the "
                                "ranks of the node measuring concurrently" % (out_bytes >> 20),
                "gpu_written_share": share, "gpu_writable_results": bool(hs["gpu_writable"]),
                "last_call_us": {k: hs[k] for k in ("call_us", "enqueued_us", "first_group_us", "workers_done_us", "gpu_share_done_us")},

@@ -14,7 +14,9 @@
  *  - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates; the library keeps
  *    only per-device constant tables);  all work is enqueued on `stream` and is asynchronous;
  *  - return value 0 = ok, >0 = cudaError_t, <0 = SPL_E_* argument error; nothing throws or exits;
- *  - functions are re-entrant for disjoint buffers; one CUDA device per process is assumed.
+ *  - one process per GPU, one calling thread: the entry points keep no per-call state besides the caller's buffers, but the
+ *    diagnostics (launch counter, spl_timing_*), the host worker pool and spl_init's per-device tables are process-wide and
+ *    unsynchronised.  spl_init() must have run on the CURRENT device (checked on every call).
  */
 #ifndef SPLENDOR_B200_H
 #define SPLENDOR_B200_H
@@ -302,8 +304,9 @@ int spl_host_free(void *ptr);
  * share landed, [5] share of the envs the GPU wrote widened, [6] worker threads, [7] 1 = result arrays GPU-writable */
 #define SPL_HOST_STATS 8
 int spl_host_get_stats(const spl_host_t *h, double *out);
-/* streaming-store rate of the worker pool in GB/s written (mode 0: fill, 1: uint8 -> int32 widening), the ceiling
- * the host-buffer path is reported against (bench.py e2e.host_store_gbs).  Pure CPU; needs no device. */
+/* sustained streaming-store rate of the worker pool in GB/s written (mode 0: fill, 1: uint8 -> int32 widening) over at
+ * least `reps` passes and 40 ms: the ceiling the host-buffer path is reported against (bench.py e2e.host_store_gbs).
+ * Pure CPU; needs no device. */
 double spl_host_store_rate(int64_t bytes_per_thread, int reps, int mode);
 
 const char *spl_error_string(int code);

@@ -1228,7 +1228,11 @@ __global__ void spl_dual_combine_kernel(const float* r1, const uint8_t* t1, cons
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
-static int g_inited_device = -1;
+static bool g_inited[64];  // per device ordinal: constant tables uploaded, kernel attributes set
+static bool device_ready() {
+	int dev = -1;
+	return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && g_inited[dev];
+}
 static int g_num_sms = 0;
 static int g_occ[3][2];  // [kernel: step, observe, rollout][wpc 1 / 4] resident CTAs per SM
 static uint64_t g_host_ret[SPL_RET_TABLE_LEN];
@@ -1329,7 +1333,8 @@ int spl_init(void) {
 	int dev = 0;
 	SPL_CUDA(cudaGetDevice(&dev));
 	load_knobs();
-	if (g_inited_device == dev) return 0;
+	if (dev < 0 || dev >= 64) return SPL_E_BADARG;
+	if (g_inited[dev]) return 0;
 	SplTables T;
 	spl_build_tables(&T);
 	if (!g_host_ret_built) {
@@ -1366,14 +1371,14 @@ int spl_init(void) {
 	SPL_SETUP((spl_rollout_kernel<4>), 2, 1, 128)
 #undef SPL_SETUP
 	SPL_CUDA(cudaDeviceSynchronize());
-	g_inited_device = dev;
+	g_inited[dev] = true;
 	return 0;
 }
 
 static int check_envs(const spl_envs_t* e) {
 	if (!e || !e->state || !e->decks || !e->episode || !e->scratch || e->n <= 0 || e->stride < e->n) return SPL_E_BADARG;
 	if (((uintptr_t)e->state & 15) || ((uintptr_t)e->decks & 15) || ((uintptr_t)e->spare & 15)) return SPL_E_ALIGN;
-	if (g_inited_device < 0) return SPL_E_NOTINIT;
+	if (!device_ready()) return SPL_E_NOTINIT;
 	return 0;
 }
 
@@ -1557,10 +1562,10 @@ static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 	}
 	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
-	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
+	if (timed) SPL_CUDA(cudaEventRecord(g_ev[2 * g_ev_used], st));
 	if (f16) SPL_LAUNCH_STEP(SPL_OUT_F16)
 	else SPL_LAUNCH_STEP(SPL_OUT_I32)
-	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
+	if (timed) SPL_CUDA(cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st));
 	g_launches++;
 	return (int)cudaGetLastError();
 }
@@ -1580,10 +1585,10 @@ int spl_launch_compact(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 	p.vec_ok = ((uintptr_t)obs_u8 & 15) == 0;
 	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
-	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
+	if (timed) SPL_CUDA(cudaEventRecord(g_ev[2 * g_ev_used], st));
 	if (spares) p.reset_mode = SPL_RESET_SPARE_INLINE;
 	SPL_LAUNCH_STEP(SPL_OUT_COMPACT)
-	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
+	if (timed) SPL_CUDA(cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st));
 	g_launches++;
 	SPL_CUDA(cudaGetLastError());
 	if (spares) return refill_spares_if_due(e, io, st);
@@ -1639,10 +1644,10 @@ int spl_rollout_random(const spl_envs_t* envs, const spl_step_io_t* io, int32_t 
 	if (groups * (int64_t)p.nchunks >= (int64_t)1 << 32) return SPL_E_BADARG;
 	SPL_CUDA(cudaMemsetAsync(envs->scratch, 0, (size_t)(4 + groups) * sizeof(int32_t), st));
 	const bool timed = g_timing && g_ev_used < SPL_TIMING_POOL;
-	if (timed) cudaEventRecord(g_ev[2 * g_ev_used], st);
+	if (timed) SPL_CUDA(cudaEventRecord(g_ev[2 * g_ev_used], st));
 	if (L.wpc == 1) spl_rollout_kernel<1><<<L.grid, 32, 0, st>>>(p);
 	else spl_rollout_kernel<4><<<L.grid, 128, 0, st>>>(p);
-	if (timed) cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st);
+	if (timed) SPL_CUDA(cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st));
 	g_launches++;
 	SPL_CUDA(cudaGetLastError());
 	// the deals the launch consumed are replaced right behind it (the launch itself never waits for a generator)
@@ -1659,7 +1664,7 @@ int spl_refill_spares(const spl_envs_t* envs, void* stream) {
 
 int spl_rollout_plan(int64_t n, int32_t steps, int32_t* out) {
 	if (n <= 0 || steps <= 0 || !out) return SPL_E_BADARG;
-	if (g_inited_device < 0) return SPL_E_NOTINIT;
+	if (!device_ready()) return SPL_E_NOTINIT;
 	LaunchShape L = launch_shape(n, 2);
 	const int64_t groups = ((n + 31) / 32 + L.wpc - 1) / L.wpc;
 	int chunk = L.chunk, nchunks = spl_num_chunks(steps, L.chunk);
@@ -1683,7 +1688,7 @@ int spl_observe_policy(const spl_envs_t* envs, void* obs_f16, uint8_t* obs_u8, i
 
 int spl_random_action(const int8_t* mask, int64_t n, uint64_t env_offset, uint64_t key, uint64_t t, int32_t* actions, void* stream) {
 	if (!mask || !actions || n <= 0) return SPL_E_BADARG;
-	if (g_inited_device < 0) return SPL_E_NOTINIT;
+	if (!device_ready()) return SPL_E_NOTINIT;
 	int64_t ctas = ((n + 31) / 32 + 3) / 4;
 	int64_t cap = (int64_t)g_num_sms * 8;
 	spl_random_action_kernel<<<(int)(ctas < cap ? ctas : cap), 128, 0, (cudaStream_t)stream>>>(mask, n, env_offset, key, t, actions);
