@@ -45,9 +45,13 @@ struct PushParams {
 	uint32_t seq;     // 31 bits
 	int32_t nibbles;  // nibble-pack the observation bytes of the CPU share
 	uint32_t* flags;  // [groups] pinned host: seq | bit 31 = this group's observation bytes are raw
-	// CPU share: staging (pinned host, device alias); s_obs may be the caller's registered uint8 array, or null
-	uint8_t* s_obs;
-	uint4* s_side;
+	// CPU share: per-worker staging rings (pinned host, device aliases), see spl_host_pool.h
+	uint8_t* ring;                        // [threads][SPL_RING_SLOTS][SPL_SLOT_BYTES]
+	unsigned long long* ring_flags;       // [threads][SPL_RING_SLOTS]
+	const unsigned long long* consumed;   // [threads][8], written by the workers
+	unsigned long long tag_base;
+	int32_t ring_slots;  // slots per worker
+	int32_t want_obs;
 	// direct share: the caller's arrays (device aliases of pinned host memory), each nullable
 	int32_t* o_obs;
 	uint8_t* o_obs_u8;
@@ -81,28 +85,40 @@ __global__ void __launch_bounds__(256) spl_push_kernel(const PushParams p) {
 	const int T = p.threads;
 	const int base = p.cpu_groups / T, rem = p.cpu_groups % T;
 	for (int k = blockIdx.x; k < p.groups; k += gridDim.x) {
-		int g = k;
+		int g = k, rr = 0, jj = 0;
 		const bool direct = k >= p.cpu_groups;
-		if (!direct) {  // push order k -> (round r, worker j) -> group start_j + r   (spl_job_share)
-			int r, j;
-			if (k < base * T) r = k / T, j = k - r * T;
-			else r = base, j = k - base * T;
-			g = j * base + min(j, rem) + r;
+		if (!direct) {  // push order k -> (round rr, worker jj) -> group start_jj + rr   (spl_job_share)
+			if (k < base * T) rr = k / T, jj = k - rr * T;
+			else rr = base, jj = k - base * T;
+			g = jj * base + min(jj, rem) + rr;
 		}
 		const int64_t lo = (int64_t)g * SPL_HOST_GROUP;
 		const int m = (int)min((int64_t)SPL_HOST_GROUP, p.n - lo);
 		const uint8_t* sb = p.d_obs + lo * SPL_OBS_DIM_;
 		const uint4* so = reinterpret_cast<const uint4*>(sb);
-		uint32_t mode = 0;
+		unsigned long long tag = 0;
+		unsigned long long* flag64 = nullptr;
 		if (!direct) {
-			if (tid == 0) s_raw = p.nibbles ? 0 : 1;
+			const int slot_i = jj * p.ring_slots + rr % p.ring_slots;
+			uint8_t* slot = p.ring + (size_t)slot_i * SPL_SLOT_BYTES;
+			tag = p.tag_base + (unsigned long long)rr + 1ull;
+			flag64 = p.ring_flags + slot_i;
+			if (tid == 0) {
+				s_raw = p.nibbles ? 0 : 1;
+				// flow control: the slot's previous occupant (round rr - SLOTS of this worker) must have been emptied.  The first
+				// SLOTS rounds of a lock-step never wait (the previous call returned only after every worker was done).
+				if (rr >= p.ring_slots) {
+					const volatile unsigned long long* c = p.consumed + 8 * jj;
+					while (*c + (unsigned long long)p.ring_slots < tag) __nanosleep(500);
+				}
+			}
 			__syncthreads();
 			for (int e = tid; e < m; e += nthr) {
 				const uint4 rec = __ldcs(p.d_side + lo + e);
 				if (rec.w & 1u) s_raw = 1;
-				p.s_side[lo + e] = rec;
+				reinterpret_cast<uint4*>(slot)[e] = rec;
 			}
-			if (p.s_obs != nullptr) {
+			if (p.want_obs) {
 				for (int q = tid; q < m * SPL_WIDE_COLS; q += nthr) {
 					const int e = q / SPL_WIDE_COLS;
 					s_wide[q] = sb[e * SPL_OBS_DIM_ + c_wide_cols[q - e * SPL_WIDE_COLS]];
@@ -110,9 +126,9 @@ __global__ void __launch_bounds__(256) spl_push_kernel(const PushParams p) {
 			}
 			__syncthreads();
 			const bool raw = s_raw != 0;
-			mode = raw ? 0x80000000u : 0u;
-			if (p.s_obs != nullptr) {
-				uint8_t* db = p.s_obs + lo * SPL_OBS_DIM_;
+			if (raw) tag |= 1ull << 63;
+			if (p.want_obs) {
+				uint8_t* db = slot + SPL_SLOT_SIDE;
 				if (raw) {
 					const int nq = (m * SPL_OBS_DIM_) >> 4;
 #pragma unroll 4
@@ -194,16 +210,25 @@ __global__ void __launch_bounds__(256) spl_push_kernel(const PushParams p) {
 		}
 		__threadfence_system();
 		__syncthreads();
-		if (tid == 0) *reinterpret_cast<volatile uint32_t*>(p.flags + g) = p.seq | mode;
+		if (tid == 0) {
+			if (direct) *reinterpret_cast<volatile uint32_t*>(p.flags + g) = p.seq;
+			else *reinterpret_cast<volatile unsigned long long*>(flag64) = tag;
+		}
 	}
 }
 
 struct spl_host {
 	int64_t n;
 	int32_t groups;
-	uint8_t *d_obs, *h_obs, *hd_obs;  // HBM | pinned staging | its device alias
-	uint4 *d_side, *hd_side;
-	uint32_t* h_side;
+	uint8_t* d_obs;   // HBM: compact outputs of the step kernel
+	uint4* d_side;
+	// per-worker staging rings in pinned host memory + device aliases (spl_host_pool.h)
+	int ring_threads;  // workers the rings were sized for
+	int ring_slots;    // slots per worker (SPL_RING_SLOTS; the environment variable of that name overrides it, diagnostics)
+	uint8_t *h_ring, *hd_ring;
+	uint64_t *h_ring_flags, *h_consumed;
+	unsigned long long *hd_ring_flags, *hd_consumed;
+	uint64_t tag_base;
 	int32_t *h_act, *hd_act;  // pinned copy of the actions | its device alias
 	uint32_t *h_flags, *hd_flags;
 	uint32_t seq;
@@ -271,13 +296,18 @@ int spl_host_create(int64_t n, int32_t chunks, spl_host_t** out) {
 	cudaError_t e = cudaGetDevice(&h->device);
 	if (e == cudaSuccess) e = cudaMalloc(&h->d_obs, (size_t)n * SPL_OBS_DIM_ + 64);
 	if (e == cudaSuccess) e = cudaMalloc(&h->d_side, (size_t)n * 16);
-	// staging: one full-size slot per group (the nibble form of a partial last group still keeps its wide bytes at +9,504)
-	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_obs, (size_t)h->groups * SPL_GROUP_OBS_BYTES + 64, fl);
-	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_side, (size_t)n * 16, fl);
+	h->ring_threads = spl_pool_threads();
+	h->ring_slots = env_int("SPL_RING_SLOTS", SPL_RING_SLOTS);
+	if (h->ring_slots < 1) h->ring_slots = 1;
+	const size_t slots = (size_t)h->ring_threads * h->ring_slots;
+	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_ring, slots * SPL_SLOT_BYTES, fl);
+	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_ring_flags, slots * 8, fl);
+	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_consumed, (size_t)h->ring_threads * 64, fl);
 	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_act, (size_t)n * 4, fl);
 	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_flags, (size_t)h->groups * 4 + 64, fl);
-	if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->hd_obs, h->h_obs, 0);
-	if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->hd_side, h->h_side, 0);
+	if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->hd_ring, h->h_ring, 0);
+	if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->hd_ring_flags, h->h_ring_flags, 0);
+	if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->hd_consumed, h->h_consumed, 0);
 	if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->hd_flags, h->h_flags, 0);
 	if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->hd_act, h->h_act, 0);
 	if (e != cudaSuccess) {  // nothing half-built is handed out (spl_host_destroy skips what was never created)
@@ -285,6 +315,10 @@ int spl_host_create(int64_t n, int32_t chunks, spl_host_t** out) {
 		return (int)e;
 	}
 	memset(h->h_flags, 0, (size_t)h->groups * 4 + 64);
+	memset(h->h_ring, 0, slots * SPL_SLOT_BYTES);
+	memset(h->h_ring_flags, 0, slots * 8);
+	memset(h->h_consumed, 0, (size_t)h->ring_threads * 64);
+	h->tag_base = 0;
 	*out = h;
 	return 0;
 }
@@ -293,8 +327,9 @@ int spl_host_destroy(spl_host_t* h) {
 	if (!h) return 0;
 	if (h->d_obs) cudaFree(h->d_obs);
 	if (h->d_side) cudaFree(h->d_side);
-	if (h->h_obs) cudaFreeHost(h->h_obs);
-	if (h->h_side) cudaFreeHost(h->h_side);
+	if (h->h_ring) cudaFreeHost(h->h_ring);
+	if (h->h_ring_flags) cudaFreeHost(h->h_ring_flags);
+	if (h->h_consumed) cudaFreeHost(h->h_consumed);
 	if (h->h_act) cudaFreeHost(h->h_act);
 	if (h->h_flags) cudaFreeHost(h->h_flags);
 	free(h);
@@ -403,14 +438,17 @@ static int host_run(spl_host_t* h, const spl_envs_t* envs, const spl_host_io_t* 
 	if (h->seq == 0) h->seq = 1;
 	p.flags = h->hd_flags, p.seq = h->seq;
 	p.nibbles = h->nibbles;
-	p.s_side = h->hd_side;
-	p.s_obs = want_obs ? h->hd_obs : nullptr;
+	p.ring = h->hd_ring, p.ring_flags = h->hd_ring_flags, p.consumed = h->hd_consumed, p.tag_base = h->tag_base;
+	p.ring_slots = h->ring_slots;
+	p.want_obs = want_obs ? 1 : 0;
 	int T = spl_pool_threads();
+	if (T > h->ring_threads) T = h->ring_threads;  // (the pool grew after this context was created)
 	int64_t direct_groups = direct_ok ? (int64_t)(h->direct_frac * h->groups + 0.5) : 0;
 	if (direct_groups > h->groups) direct_groups = h->groups;
 	p.cpu_groups = (int32_t)(h->groups - direct_groups);
 	if (T > p.cpu_groups) T = p.cpu_groups > 0 ? p.cpu_groups : 1;
 	p.threads = T;
+	for (int j = 0; j < T; j++) h->h_consumed[8 * j] = h->tag_base;  // every worker starts the lock-step with an empty ring
 	spl_push_kernel<<<h->push_ctas, h->push_threads, 0, st>>>(p);
 	g_launches++;
 	SPL_CUDA(cudaGetLastError());
@@ -418,8 +456,10 @@ static int host_run(spl_host_t* h, const spl_envs_t* envs, const spl_host_io_t* 
 
 	SplHostJob* job = spl_pool_job();
 	*job = SplHostJob();
-	job->obs_u8 = h->h_obs, job->side = h->h_side, job->io = *io, job->n = n;
-	job->packed = 1;
+	job->io = *io, job->n = n;
+	job->ring = h->h_ring, job->ring_flags = h->h_ring_flags, job->consumed = h->h_consumed, job->tag_base = h->tag_base;
+	job->ring_slots = h->ring_slots;
+	h->tag_base += (uint64_t)(p.cpu_groups / T + 1);  // tags never repeat: a stale flag cannot match a later lock-step
 	job->cpu_groups = p.cpu_groups, job->threads = T;
 	job->flags = h->h_flags, job->seq = p.seq;
 	h->poll_stream = st;

@@ -136,19 +136,19 @@ static void stream_copy(void* dst, const void* src, size_t bytes) {
 	memcpy(dst, src, bytes);
 }
 
-// widen envs [lo, hi), hi - lo <= SPL_HOST_GROUP: obs_u8 / side are the staging arrays (indexed by env), outputs are
-// the caller's arrays.  The small outputs of a group are assembled in L1 and leave as whole cache lines too (a full
+// widen envs [lo, hi), hi - lo <= SPL_HOST_GROUP: obs_lo / side_lo point at the observation bytes / records of env `lo`,
+// outputs are the caller's arrays (indexed by env).  The small outputs of a group are assembled in L1 and leave as whole cache lines too (a full
 // group is 2,880 B of mask, 256 B of rewards, ...: no read-for-ownership of the destination when it is 64-byte aligned).
-void spl_expand_block(const uint8_t* obs_u8, const uint32_t* side, int64_t lo, int64_t hi, const spl_host_io_t* io) {
-	if (io->obs) widen(obs_u8 + lo * 297, io->obs + lo * 297, (size_t)(hi - lo) * 297);
-	if (io->obs_u8 && io->obs_u8 != obs_u8) stream_copy(io->obs_u8 + lo * 297, obs_u8 + lo * 297, (size_t)(hi - lo) * 297);
+void spl_expand_block(const uint8_t* obs_lo, const uint32_t* side_lo, int64_t lo, int64_t hi, const spl_host_io_t* io) {
+	if (io->obs) widen(obs_lo, io->obs + lo * 297, (size_t)(hi - lo) * 297);
+	if (io->obs_u8 && io->obs_u8 + lo * 297 != obs_lo) stream_copy(io->obs_u8 + lo * 297, obs_lo, (size_t)(hi - lo) * 297);
 	alignas(64) int8_t mask[SPL_HOST_GROUP * 45 + 8];
 	alignas(64) float reward[SPL_HOST_GROUP];
 	alignas(64) uint8_t term[SPL_HOST_GROUP], info[SPL_HOST_GROUP];
 	alignas(64) int32_t next[SPL_HOST_GROUP];
 	const int m = (int)(hi - lo);
 	for (int i = 0; i < m; i++) {
-		const uint32_t* rec = side + 4 * (lo + i);
+		const uint32_t* rec = side_lo + 4 * i;
 		const uint32_t x = rec[0], y = rec[1], z = rec[2];
 		if (io->mask) {
 			const uint64_t mk = (uint64_t)x | ((uint64_t)(y & 0x1FFFu) << 32);
@@ -230,27 +230,35 @@ static void run_share(SplHostJob* job, int j) {
 	const bool want_obs = job->io.obs || job->io.obs_u8;
 	for (int64_t r = 0; r < len; r++) {
 		const int64_t g = start + r;
-		uint32_t f = job->seq;
-		if (job->flags) {
-			unsigned spins = 0;
-			while (((f = __atomic_load_n(job->flags + g, __ATOMIC_ACQUIRE)) & 0x7FFFFFFFu) != job->seq) {
-				if (job->abort.load(std::memory_order_relaxed)) return;
-				// worker 0 is the thread that owns the CUDA context: it watches the stream for errors while it waits
-				if (j == 0 && job->poll && (++spins & 0x3FFFu) == 0 && job->poll(job->poll_ctx)) {
-					job->abort.store(1);
-					return;
-				}
-				cpu_relax();
+		const int64_t lo = g * G, hi = lo + G < job->n ? lo + G : job->n;
+		if (job->ring == nullptr) {  // complete linear arrays (spl_host_expand)
+			spl_expand_block(job->obs_u8 ? job->obs_u8 + lo * 297 : nullptr, job->side + 4 * lo, lo, hi, &job->io);
+			continue;
+		}
+		const uint64_t want = job->tag_base + (uint64_t)r + 1u;
+		const uint64_t* flag = job->ring_flags + (size_t)j * job->ring_slots + (size_t)(r % job->ring_slots);
+		uint64_t f;
+		unsigned spins = 0;
+		while (((f = __atomic_load_n(flag, __ATOMIC_ACQUIRE)) & ~(1ull << 63)) != want) {
+			if (job->abort.load(std::memory_order_relaxed)) return;
+			// worker 0 is the thread that owns the CUDA context: it watches the stream for errors while it waits
+			if (j == 0 && job->poll && (++spins & 0x3FFFu) == 0 && job->poll(job->poll_ctx)) {
+				job->abort.store(1);
+				return;
 			}
+			cpu_relax();
 		}
 		if (r == 0) t_first = spl_now_us();
-		const int64_t lo = g * G, hi = lo + G < job->n ? lo + G : job->n;
-		if (job->packed && want_obs && !(f >> 31)) {
-			unpack_group(job->obs_u8 + lo * 297, (int)(hi - lo), tmp);
-			spl_expand_block(tmp - lo * 297, job->side, lo, hi, &job->io);
-		} else {
-			spl_expand_block(job->obs_u8, job->side, lo, hi, &job->io);
+		const uint8_t* slot = job->ring + ((size_t)j * job->ring_slots + (size_t)(r % job->ring_slots)) * SPL_SLOT_BYTES;
+		const uint32_t* side = reinterpret_cast<const uint32_t*>(slot);
+		const uint8_t* obs = slot + SPL_SLOT_SIDE;
+		if (want_obs && !(f >> 63)) {
+			unpack_group(obs, (int)(hi - lo), tmp);
+			obs = tmp;
 		}
+		spl_expand_block(obs, side, lo, hi, &job->io);
+		// every read of the slot is done (x86: loads are not reordered after a later store): the link may overwrite it
+		__atomic_store_n(job->consumed + 8 * (size_t)j, want, __ATOMIC_RELEASE);
 	}
 	job->t_first[j] = t_first;
 	job->t_done[j] = spl_now_us();
@@ -488,7 +496,7 @@ extern "C" int spl_host_expand(const uint8_t* obs_u8, const void* side, int64_t 
 	if (!side || !io || n <= 0 || ((io->obs || io->obs_u8) && !obs_u8)) return SPL_E_BADARG;
 	SplHostJob* job = spl_pool_job();
 	*job = SplHostJob();
-	job->obs_u8 = obs_u8, job->side = (const uint32_t*)side, job->io = *io, job->n = n;
+	job->obs_u8 = obs_u8, job->side = (const uint32_t*)side, job->io = *io, job->n = n;  // (no ring: the arrays are complete)
 	job->threads = spl_pool_threads();
 	job->cpu_groups = (n + SPL_HOST_GROUP - 1) / SPL_HOST_GROUP;
 	spl_pool_run();

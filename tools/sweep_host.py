@@ -1,5 +1,5 @@
 """Sweep the host-buffer path's knobs (diagnostic): worker threads x push-kernel CTAs x GPU-written share.
-usage: python tools/sweep_host.py ENVS 'THREADS,CTAS,DIRECT[,CTA_THREADS[,NIBBLES]]' ...     (DIRECT: share in [0,1], or -1 = feedback)"""
+usage: python tools/sweep_host.py ENVS 'THREADS,CTAS,DIRECT[,CTA_THREADS[,NIBBLES[,RING_SLOTS]]]' ...     (DIRECT: share in [0,1], or -1 = feedback)"""
 import os
 import sys
 import time
@@ -13,8 +13,9 @@ from splendor_gym_b200 import SplendorVecEnv
 N = int(sys.argv[1])
 dtypes = (torch.int32, torch.uint8) if os.environ.get("SWEEP_U8") else (torch.int32,)
 for spec in sys.argv[2:]:
-    parts = spec.split(",") + ["256", "1"]
-    threads, ctas, direct, cta_threads, nibbles = parts[:5]
+    parts = spec.split(",") + ["64", "1", "16"][len(spec.split(",")) - 3:]
+    threads, ctas, direct, cta_threads, nibbles, ring = parts[:6]
+    os.environ["SPL_RING_SLOTS"] = ring
     os.environ["SPL_PUSH_CTAS"] = ctas
     os.environ["SPL_PUSH_THREADS"] = cta_threads
     os.environ["SPL_HOST_NIBBLES"] = nibbles
@@ -39,7 +40,7 @@ for spec in sys.argv[2:]:
             for k, v in env.host_stats().items():
                 acc[k] = acc.get(k, 0.0) + v / reps
         el = time.perf_counter() - t0
-        print(f"envs={N} threads={threads:>2s} ctas={ctas:>3s}x{cta_threads:>3s} nib={nibbles} direct={direct:>5s} obs={str(dt):12s} {1e6 * el / reps:7.1f} us per lock-step  "
+        print(f"envs={N} threads={threads:>2s} ctas={ctas:>3s}x{cta_threads:>3s} nib={nibbles} ring={ring:>3s} direct={direct:>5s} obs={str(dt):12s} {1e6 * el / reps:7.1f} us per lock-step  "
               f"{N * reps / el / 1e6:7.2f} M env-steps/s | call {acc['call_us']:.0f} enq {acc['enqueued_us']:.0f} first {acc['first_group_us']:.0f} "
               f"workers {acc['workers_done_us']:.0f} gpu {acc['gpu_share_done_us']:.0f} share {acc['gpu_written_share']:.3f}", flush=True)
     env.close()
