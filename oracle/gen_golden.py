@@ -473,6 +473,27 @@ def gen_games_digest():
         "env_steps": sum(r[2] for r in rows)})
 
 
+def gen_games_digest_100k():
+    """The same for 100,000 games (seeds 1,000,000 ...), stored compactly: one sha256 per CHUNK of 100 games over the games'
+    (moves, winner, steps, sha) tuples, plus the totals.  ~10 min on 8 cores."""
+    import multiprocessing as mp
+
+    seed0, games, chunk = 1_000_000, 100_000, 100
+    with mp.get_context("fork").Pool(len(os.sched_getaffinity(0))) as pool:
+        rows = pool.map(lcg_game_digest, range(seed0, seed0 + games), chunksize=100)
+    chunks = []
+    for c in range(0, games, chunk):
+        h = hashlib.sha256()
+        for r in rows[c:c + chunk]:
+            h.update(("%d,%d,%d,%s;" % tuple(r)).encode())
+        chunks.append(h.hexdigest()[:16])
+    dump("games_digest_100k.json", {
+        "policy": "lcg (see games_digest.json)", "record": "see games_digest.json", "seed0": seed0, "games": games, "chunk": chunk,
+        "chunk_digest": "sha256 over '%d,%d,%d,%s;' % (moves, winner, steps, game sha) of the chunk's games, first 16 hex digits",
+        "chunks": chunks, "env_steps": sum(r[2] for r in rows), "max_steps": max(r[2] for r in rows),
+        "winners": [sum(1 for r in rows if r[1] == w) for w in (0, 1, -1)]})
+
+
 # ----------------------------------------------------------------------------- wrappers.json
 def pick(obs, mask, mul: int, add: int) -> int:
     """Deterministic stand-in policy, a function of (obs, mask) only: the k-th legal action, k = (sum(obs) * mul + add) mod #legal."""

@@ -28,6 +28,28 @@ __device__ SplTables g_tables;
 __device__ unsigned int g_sm_units[256];  // diagnostic build (tools/sm_units.py): warp-lock-steps processed per SM
 #endif
 __device__ uint64_t g_ret_table[SPL_RET_TABLE_LEN];
+#ifdef SPL_DEBUG_PHASES
+// diagnostic build (tools/step_phases.py): per-warp SM-clock stamps at the phase boundaries of the single-step kernel
+#define SPL_PHASE_SLOTS 13
+#define SPL_PHASE_WARPS 65536
+__device__ unsigned long long g_phase[SPL_PHASE_SLOTS][SPL_PHASE_WARPS];
+__device__ __forceinline__ void spl_phase_stamp(int k) {
+	if ((threadIdx.x & 31) == 0) {
+		const unsigned wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+		unsigned long long t;
+		if (k == 10 || k == 12) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+		else if (k == 11) {
+			unsigned sm;
+			asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+			t = sm;
+		} else asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+		if (wid < SPL_PHASE_WARPS) g_phase[k][wid] = t;
+	}
+}
+#define SPL_PH(k) spl_phase_stamp(k)
+#else
+#define SPL_PH(k)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11) -- counter-based stream for action sampling and native shuffles
@@ -487,13 +509,16 @@ __device__ __forceinline__ int32_t spl_tile_emit(const StepParams& p, const SplT
 		sampled = spl_sample_action(m, p.action_key, p.env_offset + (uint64_t)env, t);
 		if (valid) next_action[env] = sampled;
 	}
+	SPL_PH(6);
 	if (obs != nullptr) {
 		SplObsStager stage(tl.smem, lane, w[0]);
 		spl_encode_observation(w, s, tl.T, stage);
 		__syncwarp();
+		SPL_PH(7);
 		spl_store_obs_tile(obs + tl.ti * 32 * SPL_OBS_DIM, tl.smem, lane, tl.rows, p.vec_ok);
 		__syncwarp();
 	}
+	SPL_PH(8);
 	return sampled;
 }
 
@@ -549,7 +574,11 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 	__shared__ SplTables Ts;
 	__shared__ __align__(16) uint32_t tiles[WPC][SPL_TILE_WORDS];
 	SplTile tl;
+	SPL_PH(0);
+	SPL_PH(10);
+	SPL_PH(11);
 	tl.T = spl_stage_tables<WPC * 32>(&Ts);
+	SPL_PH(1);
 	tl.lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	tl.smem = tiles[warp];
@@ -568,7 +597,12 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 		r.reward = 0.0f, r.terminated = 0, r.info = 0;
 		if (DO_STEP) {
 			const bool act = valid && (p.active == nullptr || p.active[env] != 0);
+#ifdef SPL_DEBUG_PHASES
+			if (__shfl_xor_sync(SPL_FULL, w[0] + (act ? p.actions[env] : 0), 1) == 0xdeadbeefu) return;  // forces the loads to have landed
+			SPL_PH(2);
+#endif
 			spl_tile_step<false>(p, tl, s, act, act ? p.actions[env] : 0, env, r);
+			SPL_PH(3);
 			if (act) {
 				spl_pack(s, w);
 				spl_store_state(p, env, w);
@@ -579,8 +613,13 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 				p.info[env] = (uint8_t)r.info;
 			}
 		}
+		SPL_PH(4);
 		uint64_t m = 0;
 		if (COMPACT || p.mask != nullptr || p.next_action != nullptr) m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, tl.T);
+#ifdef SPL_DEBUG_PHASES
+		if (__shfl_xor_sync(SPL_FULL, (uint32_t)m, 1) == 0xdeadbeefu && m == 0x123456789ull) return;  // forces the mask to be complete
+		SPL_PH(5);
+#endif
 		if (COMPACT) {
 			const int32_t sampled = spl_sample_action(m, p.action_key, p.env_offset + (uint64_t)env, t);
 			SplObsStager stage(tl.smem, tl.lane, w[0]);
@@ -606,6 +645,8 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 				__syncwarp();
 			}
 		}
+		SPL_PH(9);
+		SPL_PH(12);
 	}
 }
 
@@ -1297,6 +1338,15 @@ int spl_timing_read(double* total_ms, int64_t* count) {
 }
 
 int64_t spl_launch_count(void) { return g_launches; }
+
+#ifdef SPL_DEBUG_PHASES
+int spl_debug_phases(unsigned long long* out, int warps) {  // out[SPL_PHASE_SLOTS][warps]
+	SPL_CUDA(cudaDeviceSynchronize());
+	for (int k = 0; k < SPL_PHASE_SLOTS; k++)
+		SPL_CUDA(cudaMemcpyFromSymbol(out + (size_t)k * warps, g_phase, sizeof(unsigned long long) * warps, sizeof(unsigned long long) * SPL_PHASE_WARPS * k));
+	return 0;
+}
+#endif
 
 
 #ifdef SPL_DEBUG_SM_UNITS

@@ -40,3 +40,14 @@ def game_shas(records, steps):
     """records [T, n, REC] uint8, steps [n] -> first 16 hex digits of sha256 over each game's first steps[i] records."""
     by_game = np.ascontiguousarray(records.transpose(1, 0, 2))
     return [hashlib.sha256(by_game[i, : steps[i]].tobytes()).hexdigest()[:16] for i in range(by_game.shape[0])]
+
+
+def chunk_digests(moves, winner, steps, shas, chunk):
+    """games_digest_100k.json: sha256 over '%d,%d,%d,%s;' % (moves, winner, steps, game sha) of every `chunk` games."""
+    out = []
+    for c in range(0, len(shas), chunk):
+        h = hashlib.sha256()
+        for i in range(c, min(len(shas), c + chunk)):
+            h.update(("%d,%d,%d,%s;" % (int(moves[i]), int(winner[i]), int(steps[i]), shas[i])).encode())
+        out.append(h.hexdigest()[:16])
+    return out

@@ -672,19 +672,14 @@ def test_unaligned_output_buffers_and_strided_state(VecEnv, oracle):
     assert np.array_equal(rows, ref.export_rows())
 
 
-def test_ten_thousand_reference_games_by_digest(VecEnv):
-    """CUDA directly against the reference at volume: the 10,000 games of tests/golden/games_digest.json (773,764 env-steps
-    played by the unmodified Python engine under the LCG policy) replayed on the GPU, one env per game, in lock-step.
-    The policy runs on the device from the kernel's own masks; every step's observation, mask, reward, terminated flag and
-    info bits go into the game's sha256, which must equal the reference's, as must move counts and winners."""
+def _gpu_digest_games(VecEnv, seeds, T):
+    """Play the LCG-policy games of `seeds` on the GPU, one env per game in lock-step (policy on the device from the kernel's
+    own masks); returns (moves, winner, steps, per-game sha256) -- see tests/digest_util.py for the record layout."""
     import digest_util as D
 
-    G = load_golden("games_digest.json")
-    games = np.array([g[:3] for g in G["games"]], np.int64)
-    n, T = len(games), int(games[:, 2].max())
-    seeds = G["seed0"] + np.arange(n, dtype=np.int64)
+    n = len(seeds)
     env = VecEnv(n, shuffle="mt19937", autoreset=False)
-    _, info = env.reset(seeds=torch.from_numpy(seeds))
+    _, info = env.reset(seeds=torch.from_numpy(seeds.astype(np.int64)))
     dev = env.device
     x = torch.from_numpy(D.lcg_seed(seeds).astype(np.int64)).to(dev)
     mask = info["action_mask"]
@@ -711,10 +706,36 @@ def test_ten_thousand_reference_games_by_digest(VecEnv):
     assert int(env.obs.max()) < 256
     rows = _np(env.export_state())
     st = _np(steps)
-    assert np.array_equal(st, games[:, 2]) and np.array_equal(rows[:, 72], games[:, 0]) and np.array_equal(rows[:, 74], games[:, 1])
-    shas = D.game_shas(_np(recs), st)
+    return rows[:, 72].copy(), rows[:, 74].copy(), st, D.game_shas(_np(recs), st)
+
+
+def test_ten_thousand_reference_games_by_digest(VecEnv):
+    """CUDA directly against the reference at volume: the 10,000 games of tests/golden/games_digest.json (773,764 env-steps
+    played by the unmodified Python engine under the LCG policy) replayed on the GPU.  Every step's observation, mask, reward,
+    terminated flag and info bits go into the game's sha256, which must equal the reference's, as must move counts and winners."""
+    G = load_golden("games_digest.json")
+    games = np.array([g[:3] for g in G["games"]], np.int64)
+    n = len(games)
+    moves, winner, st, shas = _gpu_digest_games(VecEnv, G["seed0"] + np.arange(n, dtype=np.int64), int(games[:, 2].max()))
+    assert np.array_equal(st, games[:, 2]) and np.array_equal(moves, games[:, 0]) and np.array_equal(winner, games[:, 1])
     bad = [i for i in range(n) if shas[i] != G["games"][i][3]]
     assert not bad, f"{len(bad)} of {n} game digests differ from the reference, first: seed {G['seed0'] + bad[0]}"
+
+
+def test_hundred_thousand_reference_games_by_chunk_digest(VecEnv):
+    """... and the 100,000 games (7,732,816 env-steps) of tests/golden/games_digest_100k.json, in slices of 25,000 envs."""
+    import digest_util as D
+
+    G = load_golden("games_digest_100k.json")
+    got, total = [], 0
+    for lo in range(0, G["games"], 25000):
+        seeds = G["seed0"] + np.arange(lo, min(G["games"], lo + 25000), dtype=np.int64)
+        moves, winner, st, shas = _gpu_digest_games(VecEnv, seeds, G["max_steps"])
+        got += D.chunk_digests(moves, winner, st, shas, G["chunk"])
+        total += int(st.sum())
+    bad = [i for i, (a, b) in enumerate(zip(got, G["chunks"])) if a != b]
+    assert not bad and len(got) == len(G["chunks"]), f"{len(bad)} of {len(got)} chunk digests differ from the reference, first chunk {bad[:1]}"
+    assert total == G["env_steps"]
 
 
 def test_rollout_without_observations_matches_oracle(VecEnv, oracle):

@@ -152,16 +152,10 @@ def test_vec_lockstep_autoreset_matches_single(oracle):
     assert v.stats()[0] == sum(ep)
 
 
-def test_ten_thousand_reference_games_by_digest(oracle):
-    """tests/golden/games_digest.json: 10,000 games (773,764 env-steps) played by the UNMODIFIED reference under the LCG
-    policy, one sha256 per game over every step's observation, mask, reward, terminated flag and info bits.  The oracle
-    replays them all in lock-step and must reproduce every digest, move count and winner."""
+def _oracle_digest_games(oracle, seeds, T):
     import digest_util as D
 
-    G = load_golden("games_digest.json")
-    games = np.array([g[:3] for g in G["games"]], np.int64)
-    n, T = len(games), int(games[:, 2].max())
-    seeds = G["seed0"] + np.arange(n, dtype=np.uint64)
+    n = len(seeds)
     v = oracle.OracleVec(n)
     _, mask = v.reset(seeds=seeds)
     x = D.lcg_seed(seeds)
@@ -177,10 +171,37 @@ def test_ten_thousand_reference_games_by_digest(oracle):
         active &= term == 0
     assert not active.any()
     rows = v.export_rows()
-    assert np.array_equal(steps, games[:, 2]) and np.array_equal(rows[:, 72], games[:, 0]) and np.array_equal(rows[:, 74], games[:, 1])
-    shas = D.game_shas(recs, steps)
+    return rows[:, 72].copy(), rows[:, 74].copy(), steps, D.game_shas(recs, steps)
+
+
+def test_ten_thousand_reference_games_by_digest(oracle):
+    """tests/golden/games_digest.json: 10,000 games (773,764 env-steps) played by the UNMODIFIED reference under the LCG
+    policy, one sha256 per game over every step's observation, mask, reward, terminated flag and info bits.  The oracle
+    replays them all in lock-step and must reproduce every digest, move count and winner."""
+    G = load_golden("games_digest.json")
+    games = np.array([g[:3] for g in G["games"]], np.int64)
+    n = len(games)
+    moves, winner, steps, shas = _oracle_digest_games(oracle, G["seed0"] + np.arange(n, dtype=np.uint64), int(games[:, 2].max()))
+    assert np.array_equal(steps, games[:, 2]) and np.array_equal(moves, games[:, 0]) and np.array_equal(winner, games[:, 1])
     bad = [i for i in range(n) if shas[i] != G["games"][i][3]]
     assert not bad, f"{len(bad)} of {n} game digests differ, first: seed {G['seed0'] + bad[0]}"
+
+
+def test_hundred_thousand_reference_games_by_chunk_digest(oracle):
+    """tests/golden/games_digest_100k.json: 100,000 further reference games (7.7e6 env-steps), stored as one digest per 100
+    games.  Replayed by the oracle in slices of 20,000 envs."""
+    import digest_util as D
+
+    G = load_golden("games_digest_100k.json")
+    got, total = [], 0
+    for lo in range(0, G["games"], 20000):
+        seeds = G["seed0"] + np.arange(lo, min(G["games"], lo + 20000), dtype=np.uint64)
+        moves, winner, steps, shas = _oracle_digest_games(oracle, seeds, G["max_steps"])
+        got += D.chunk_digests(moves, winner, steps, shas, G["chunk"])
+        total += int(steps.sum())
+    bad = [i for i, (a, b) in enumerate(zip(got, G["chunks"])) if a != b]
+    assert not bad and len(got) == len(G["chunks"]), f"{len(bad)} of {len(got)} chunk digests differ, first chunk {bad[:1]}"
+    assert total == G["env_steps"]
 
 
 def test_logger_strings_and_can_afford_match_the_reference():

@@ -1,4 +1,7 @@
-"""Diagnostic (needs a -DSPL_DEBUG_PHASES build selected with SPL_LIB): per-warp SM-clock stamps at the phase boundaries
+"""Diagnostic (needs a -DSPL_DEBUG_PHASES build selected with SPL_LIB:
+  cd splendor_gym_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --compiler-options -fPIC,-pthread -shared
+      -DSPL_DEBUG_PHASES -o ../libsplendor_b200_phases.so spl_kernels.cu spl_policy.cu spl_host.cu spl_host_expand.cpp -lpthread
+  SPL_LIB=splendor_gym_b200/libsplendor_b200_phases.so python tools/step_phases.py 65536): per-warp SM-clock stamps at the phase boundaries
 of the single-step kernel -> where one lock-step's time goes (table staging, state load, rules, mask, encode, stores)."""
 import ctypes as C
 import os
