@@ -49,4 +49,11 @@ for a in acc[-3:]:
     # per-warp end time relative to the kernel start (globaltimer)
     e = (g1 - g0.min()) / 1e3
     s = (g0 - g0.min()) / 1e3
+    # what the slow tail is made of: the last warps to finish, and the span if every warp's rules phase had taken the median
+    rules = c[3] - c[2]
+    clk = (c[9] - c[0]).astype(np.float64) / np.maximum((g1 - g0).astype(np.float64), 1.0)  # cycles per ns, per warp
+    est = (g1 - g0.min()) / 1e3 - np.maximum(rules - np.median(rules), 0) / np.median(clk) / 1e3
+    late = np.argsort(e)[-max(1, len(e) // 100):]
+    print(f"  slowest 1 % of warps: rules {rules[late].mean():.0f} cycles (all: {rules.mean():.0f}), obs stores {(c[8] - c[7])[late].mean():.0f} (all: {(c[8] - c[7]).mean():.0f}); "
+          f"span with every rules phase capped at its median: {est.max():.1f} us")
     print(f"  warp start us: p50 {np.percentile(s, 50):.1f} p90 {np.percentile(s, 90):.1f} max {s.max():.1f} | warp end us: p10 {np.percentile(e, 10):.1f} p50 {np.percentile(e, 50):.1f} p90 {np.percentile(e, 90):.1f} max {e.max():.1f}")
