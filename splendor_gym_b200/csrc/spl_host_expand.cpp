@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <time.h>
 
 #include <atomic>
@@ -424,11 +425,16 @@ extern "C" double spl_host_store_rate(int64_t bytes_per_thread, int reps, int mo
 	const int T = P->threads;
 	if (bytes_per_thread < 4096) bytes_per_thread = 4096;
 	bytes_per_thread &= ~(int64_t)4095;
-	char* dst = nullptr;
+	// destination like the path's result arrays (spl_host_alloc): 2 MB-aligned anonymous memory, huge pages requested
+	const size_t huge = (size_t)2 << 20;
+	const size_t dst_len = ((size_t)bytes_per_thread * T + huge - 1) / huge * huge + huge;
+	void* raw = mmap(nullptr, dst_len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+	if (raw == MAP_FAILED) return 0.0;
+	char* dst = (char*)(((uintptr_t)raw + huge - 1) / huge * huge);
+	madvise(dst, dst_len - huge, MADV_HUGEPAGE);
 	uint8_t* src = nullptr;
-	if (posix_memalign((void**)&dst, 4096, (size_t)bytes_per_thread * T)) return 0.0;
 	if (posix_memalign((void**)&src, 4096, (size_t)bytes_per_thread / 4 * T)) {
-		free(dst);
+		munmap(raw, dst_len);
 		return 0.0;
 	}
 	memset(dst, 0, (size_t)bytes_per_thread * T);
@@ -468,7 +474,7 @@ extern "C" double spl_host_store_rate(int64_t bytes_per_thread, int reps, int mo
 		passes++;
 	}
 	best = passes > 0 ? (double)bytes_per_thread * T * passes / total_us * 1e-3 : 0.0;
-	free(dst);
+	munmap(raw, dst_len);
 	free(src);
 	return best;
 }

@@ -84,3 +84,49 @@ def test_bench_reference_arm_multi_rank():
     line = json.loads(outs[0].splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["n_gpus"] == 2
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and outs[1] == ""
+
+
+HOST_WORKER = r"""
+import os, sys, json, ctypes as C
+sys.path.insert(0, %(root)r)
+import numpy as np
+from splendor_gym_b200 import _lib
+lib = _lib.load()
+threads = lib.spl_host_set_threads(0)          # default pool of this rank
+n = 5000 + 64 * int(os.environ["LOCAL_RANK"])
+rng = np.random.default_rng(n)
+obs8 = rng.integers(0, 256, size=(n, 297), dtype=np.uint8)
+mbits = rng.integers(0, 1 << 45, size=n, dtype=np.uint64)
+side = np.zeros((n, 4), np.uint32)
+side[:, 0] = (mbits & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+side[:, 1] = (mbits >> np.uint64(32)).astype(np.uint32) | (np.uint32(1) << 16)
+obs, mask, rew = np.zeros((n, 297), np.int32), np.zeros((n, 45), np.int8), np.zeros(n, np.float32)
+io = _lib.SplHostIO(obs=obs.ctypes.data, mask=mask.ctypes.data, reward=rew.ctypes.data)
+for _ in range(20):
+    assert lib.spl_host_expand(obs8.ctypes.data, side.ctypes.data, n, C.byref(io)) == 0
+want = ((mbits[:, None] >> np.arange(45, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.int8)
+ok = bool(np.array_equal(obs, obs8.astype(np.int32)) and np.array_equal(mask, want) and np.all(rew == 1.0))
+rate = lib.spl_host_store_rate(1 << 20, 2, 1)
+print(json.dumps({"threads": threads, "ok": ok, "rate_positive": rate > 0, "cores": len(os.sched_getaffinity(0))}))
+"""
+
+
+def test_host_pool_under_two_local_ranks(tmp_path):
+    """The host half of the host-buffer path (worker pool, per-rank core slices, widening) with two ranks of one node running at
+    the same time: each rank sizes its pool from its share of the cores (3/4 of cores / LOCAL_WORLD_SIZE), pins its workers
+    inside its own slice and widens correctly; the caller's affinity mask is left as it was."""
+    script = tmp_path / "host_worker.py"
+    script.write_text(HOST_WORKER % {"root": ROOT})
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), LOCAL_WORLD_SIZE="2")
+        env.pop("SPL_HOST_THREADS", None)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    cores = len(os.sched_getaffinity(0))
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-2000:]
+        rec = json.loads(out.strip().splitlines()[-1])
+        assert rec["ok"] and rec["rate_positive"]
+        assert rec["threads"] == max(1, min(32, ((cores // 2) * 3 + 3) // 4))
+        assert rec["cores"] == cores  # the calling thread's mask is restored after the rank-local first touch
