@@ -256,12 +256,13 @@ int spl_gae(const float *rewards, const float *values, const uint8_t *terminals,
 /* ---- host-buffer entry points ---------------------------------------------------------------------
  * The reference's callers live on the host: SplendorEnv.step returns NumPy arrays (envs/splendor_env.py:51-90)
  * and the vector loop stacks them (ppo_splendor.py:235-285).  These calls take HOST pointers for actions and
- * results.  Per lock-step they move 4 B/env to the device and 313 B/env back (observation as bytes + one
- * 16-byte record: 45 legal-mask bits, reward code, terminated, info, sampled next action) instead of the
- * 1,243 B/env of the reference-typed arrays; the device->host copy is cut into chunks and host threads widen
- * chunk c (uint8 -> int32 observation, bits -> int8 mask, code -> float reward) while chunk c+1 is in flight.
- * Results in the caller's buffers are exactly those of spl_step / spl_observe. */
-typedef struct spl_host spl_host_t; /* opaque: compact device buffers, pinned staging, events */
+ * results.  Per lock-step the step kernel reads 4 B/env of actions from pinned host memory and a push kernel stores the
+ * results over PCIe in 64-env groups: in a transfer form of 181.5 B/env (observation entries as nibbles + the 17 columns
+ * that can exceed 15 as bytes + one 16-byte record: 45 legal-mask bits, reward code, terminated, info, sampled next action)
+ * for the share that pinned host threads widen into the reference-typed arrays (uint8 -> int32 observation, bits -> int8
+ * mask, code -> float reward), and ALREADY WIDENED (1,243 B/env) for the rest when the result arrays are GPU-writable
+ * (spl_host_alloc).  Results in the caller's buffers are exactly those of spl_step / spl_observe. */
+typedef struct spl_host spl_host_t; /* opaque: compact device buffers, pinned staging rings + arrival flags, the split's state */
 
 typedef struct spl_host_io {
 	const int32_t *actions; /* [n] host (ignored by spl_host_observe) */
@@ -279,7 +280,7 @@ typedef struct spl_host_io {
 	int32_t reserved_;
 } spl_host_io_t;
 
-int spl_host_create(int64_t n, int32_t chunks, spl_host_t **out); /* chunks <= 0: library default */
+int spl_host_create(int64_t n, int32_t chunks, spl_host_t **out); /* chunks: ignored since ABI 120 (arrival is tracked per 64-env group) */
 int spl_host_destroy(spl_host_t *h);
 /* SplendorEnv.step for every env with host buffers; returns when the caller's buffers are filled */
 int spl_host_step(spl_host_t *h, const spl_envs_t *envs, const spl_host_io_t *io, void *stream);

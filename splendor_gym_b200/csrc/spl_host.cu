@@ -238,7 +238,7 @@ struct spl_host {
 	// split between the link and the cores
 	double direct_frac;      // share of the groups the GPU writes already widened
 	int direct_fixed;        // SPL_HOST_DIRECT set: no feedback
-	// device aliases of the caller's arrays (cached: cudaPointerGetAttributes costs ~1 us per pointer)
+	// device aliases of the caller's arrays, looked up on every call
 	spl_host_io_t seen_io;
 	PushParams seen_dev;
 	int seen_ok;
