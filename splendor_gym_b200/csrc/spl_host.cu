@@ -349,23 +349,22 @@ int spl_host_alloc(size_t bytes, void** out) {
 	uintptr_t a = ((uintptr_t)p + huge - 1) / huge * huge;
 	if (a == (uintptr_t)p) a += huge;  // room for the header below the aligned block
 	madvise((void*)a, len, MADV_HUGEPAGE);
-	size_t* hdr = (size_t*)(a - 2 * sizeof(size_t));
+	size_t* hdr = (size_t*)(a - 3 * sizeof(size_t));
 	hdr[0] = (size_t)((uintptr_t)p), hdr[1] = len + huge;
 	memset((void*)a, 0, len);  // fault the pages in (as huge pages where the kernel grants them) before pinning
+	// A box that refuses to pin this much memory still gets its arrays: spl_host_step then sees that they are not
+	// GPU-writable and lets host threads widen everything.
 	cudaError_t e = cudaHostRegister((void*)a, len, cudaHostRegisterMapped | cudaHostRegisterPortable);
-	if (e != cudaSuccess) {
-		cudaGetLastError();
-		munmap(p, len + huge);
-		return (int)e;
-	}
+	if (e != cudaSuccess) cudaGetLastError();
+	hdr[2] = e == cudaSuccess ? 1 : 0;
 	*out = (void*)a;
 	return 0;
 }
 
 int spl_host_free(void* ptr) {
 	if (!ptr) return 0;
-	cudaHostUnregister(ptr);
-	size_t* hdr = (size_t*)((uintptr_t)ptr - 2 * sizeof(size_t));
+	size_t* hdr = (size_t*)((uintptr_t)ptr - 3 * sizeof(size_t));
+	if (hdr[2] && cudaHostUnregister(ptr) != cudaSuccess) cudaGetLastError();
 	munmap((void*)(uintptr_t)hdr[0], hdr[1]);
 	return 0;
 }

@@ -137,3 +137,19 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises((SplendorB200Error, RuntimeError, AssertionError)):
         SplendorVecEnv(4, device="cpu")
+
+
+def test_host_alloc_returns_aligned_zeroed_memory_even_without_a_device(lib):
+    """spl_host_alloc: 2 MB-aligned, zeroed, writable host memory.  Without a CUDA device the pinning step fails and the block is
+    handed out unpinned (spl_host_step would then widen everything on the host) -- allocation itself must not fail."""
+    p = C.c_void_p()
+    assert lib.spl_host_alloc(C.c_size_t(3 * 1188 * 64 + 5), C.byref(p)) == 0 and p.value
+    assert p.value % (2 << 20) == 0
+    buf = (C.c_uint8 * (3 * 1188 * 64 + 5)).from_address(p.value)
+    a = np.frombuffer(buf, dtype=np.uint8)
+    assert not a.any()
+    a[:] = 7
+    assert int(a.sum()) == 7 * a.size
+    del a, buf
+    assert lib.spl_host_free(p) == 0
+    assert lib.spl_host_alloc(C.c_size_t(0), C.byref(p)) == -1
