@@ -651,6 +651,120 @@ __global__ void __launch_bounds__(WPC * 32) spl_step_kernel(const StepParams p) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Single-step kernel, two warps per tile (EXPERIMENT, off by default: knob SPL_STEP_PAIRED=1; int32 observation output).
+// Measured on B200 at 65,536 envs, same box, alternating runs: 26.17 us per lock-step against 24.78 us for the one-warp-per-tile
+// kernel below (-5.6 %), bit-exact.  Kept as the record of that experiment.
+// At 65,536 envs there are 4.6 warp slots per tile, but the rules need ~96 registers, which caps residency at 20 one-warp
+// CTAs per SM.  Here a CTA is two warpgroups handling four tiles: warps 0-3 run the rules (state load, step, fused
+// auto-reset, state store, observation encode) with a raised register budget, warps 4-7 are their helpers (legal mask of
+// the new state, sampler, mask tile, half of the observation-tile stores) with a lowered one (setmaxnreg), so that four CTAs
+// = 16 tiles fit an SM in one wave and a tile's mask / encode / store phases overlap instead of queueing in one warp.
+// Hand-over per tile through shared memory: the packed state (16 words per lane) behind named barrier 1+k, the staged
+// observation tile behind named barrier 5+k.  Same lane-local code (spl_core.cuh), same results bit for bit.
+// ------------------------------------------------------------------------------------------------
+#define SPL_PAIR_TILES 4
+#define SPL_PAIR_REGS_RULES 88
+#define SPL_PAIR_REGS_HELPER 40
+
+__device__ __forceinline__ void spl_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void spl_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// every other 512-byte store of the tile (the two warps of a tile take the even / the odd ones)
+__device__ __forceinline__ void spl_store_obs_tile_half(int32_t* gtile, const uint32_t* tile, int lane, int half) {
+#pragma unroll 2
+	for (int q = lane + 32 * half; q < SPL_TILE_WORDS; q += 64) {
+		const uint32_t v = tile[q];
+		__stcs(reinterpret_cast<int4*>(gtile) + q, make_int4((int)__byte_perm(v, 0, 0x4440), (int)__byte_perm(v, 0, 0x4441),
+		                                                     (int)__byte_perm(v, 0, 0x4442), (int)__byte_perm(v, 0, 0x4443)));
+	}
+}
+
+template <bool DO_STEP>
+__global__ void __launch_bounds__(SPL_PAIR_TILES * 64, 4) spl_step_paired_kernel(const StepParams p) {
+	__shared__ SplTables Ts;
+	__shared__ __align__(16) uint32_t tiles[SPL_PAIR_TILES][SPL_TILE_WORDS];
+	__shared__ uint32_t packed[SPL_PAIR_TILES][16][32];  // word-major: lane-consecutive, conflict-free
+	SplTile tl;
+	tl.T = spl_stage_tables<SPL_PAIR_TILES * 64>(&Ts);
+	tl.lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int k = warp & (SPL_PAIR_TILES - 1);
+	const bool helper = warp >= SPL_PAIR_TILES;
+	tl.smem = tiles[k];
+	const int64_t ntiles = (p.n + 31) >> 5;
+	const uint64_t t = p.action_t + (p.action_t_base ? *p.action_t_base : 0ull);
+	tl.ti = (int64_t)blockIdx.x * SPL_PAIR_TILES + k;
+	const bool live = tl.ti < ntiles;  // (uniform per tile: both warps of a dead tile skip the hand-over)
+	const int64_t env = tl.ti * 32 + tl.lane;
+	const bool valid = live && env < p.n;
+	tl.rows = live ? (int)min((int64_t)32, p.n - tl.ti * 32) : 0;
+	const bool want_mask = p.mask != nullptr || p.next_action != nullptr;
+	if (!helper) {
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SPL_PAIR_REGS_RULES));
+		if (!live) return;
+		uint32_t w[16];
+		spl_load_state(p, env, valid, w);
+		SplState s;
+		spl_unpack(w, s);
+		SplStepResult r;
+		r.reward = 0.0f, r.terminated = 0, r.info = 0;
+		if (DO_STEP) {
+			const bool act = valid && (p.active == nullptr || p.active[env] != 0);
+			spl_tile_step<false>(p, tl, s, act, act ? p.actions[env] : 0, env, r);
+			if (act) {
+				spl_pack(s, w);
+				spl_store_state(p, env, w);
+			}
+			if (valid) {
+				p.reward[env] = r.reward;
+				p.terminated[env] = (uint8_t)r.terminated;
+				p.info[env] = (uint8_t)r.info;
+			}
+		}
+		if (want_mask) {  // hand the new state to the helper warp
+#pragma unroll
+			for (int j = 0; j < 16; j++) packed[k][j][tl.lane] = w[j];
+			__threadfence_block();
+			spl_bar_arrive(1 + k, 64);
+		}
+		if (p.obs != nullptr) {
+			SplObsStager stage(tl.smem, tl.lane, w[0]);
+			spl_encode_observation(w, s, tl.T, stage);
+			__threadfence_block();
+			spl_bar_sync(5 + k, 64);  // tile staged: both warps stream it out
+			int32_t* g = p.obs + tl.ti * 32 * SPL_OBS_DIM;
+			if (tl.rows == 32 && p.vec_ok) spl_store_obs_tile_half(g, tl.smem, tl.lane, 0);
+			else spl_store_obs_tile(g, tl.smem, tl.lane, tl.rows, false);
+		}
+	} else {
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SPL_PAIR_REGS_HELPER));
+		if (!live) return;
+		if (want_mask) {
+			spl_bar_sync(1 + k, 64);
+			uint32_t w[16];
+#pragma unroll
+			for (int j = 0; j < 16; j++) w[j] = packed[k][j][tl.lane];
+			SplState s;
+			spl_unpack(w, s);
+			const uint64_t m = spl_is_terminal(s) ? 0ull : spl_legal_mask(s, tl.T);
+			if (p.mask != nullptr) {
+				if (p.vec_ok) spl_store_mask_tile(p.mask + tl.ti * 32 * SPL_NUM_ACTIONS, m, tl.lane, tl.rows);
+				else if (valid)
+					for (int a = 0; a < SPL_NUM_ACTIONS; a++) p.mask[env * SPL_NUM_ACTIONS + a] = (int8_t)((m >> a) & 1);
+			}
+			if (p.next_action != nullptr) {
+				const int32_t sampled = spl_sample_action(m, p.action_key, p.env_offset + (uint64_t)env, t);
+				if (valid) p.next_action[env] = sampled;
+			}
+		}
+		if (p.obs != nullptr) {
+			spl_bar_sync(5 + k, 64);
+			if (tl.rows == 32 && p.vec_ok) spl_store_obs_tile_half(p.obs + tl.ti * 32 * SPL_OBS_DIM, tl.smem, tl.lane, 1);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // Rollout work queue.  SM store bandwidth on B200 is NOT uniform: a store-only microbenchmark
 // (tools/microbench/store_bw.cu) hands 8 SMs ~2,200 tiles, ~108 SMs ~1,850 and 32 SMs ~1,430 when tiles are
 // taken from an atomic counter, and reaches 7.3-7.5 TB/s that way against 6.0-6.4 TB/s for any static split
@@ -1295,8 +1409,8 @@ static int g_ev_created = 0, g_ev_used = 0, g_timing = 0;
 	} while (0)
 
 // Tuning knobs (environment variables, diagnostics only): read once per spl_init() call, not per launch.
-enum { K_DEAL_BATCH, K_DEAL_MAX_OUTPUTS, K_ROLLOUT_CHUNK, K_ROLLOUT_CTAS_PER_SM, K_ROLLOUT_SYNC, K_SPARE_REFILL_AGE, K_SPARE_WORKLIST, K_STEP_PERSISTENT, K_STEP_WPC, K_WPC, K_COUNT };
-static const char* const g_knob_names[K_COUNT] = {"SPL_DEAL_BATCH", "SPL_DEAL_MAX_OUTPUTS", "SPL_ROLLOUT_CHUNK", "SPL_ROLLOUT_CTAS_PER_SM", "SPL_ROLLOUT_SYNC", "SPL_SPARE_REFILL_AGE", "SPL_SPARE_WORKLIST", "SPL_STEP_PERSISTENT", "SPL_STEP_WPC", "SPL_WPC"};
+enum { K_STEP_PAIRED, K_DEAL_BATCH, K_DEAL_MAX_OUTPUTS, K_ROLLOUT_CHUNK, K_ROLLOUT_CTAS_PER_SM, K_ROLLOUT_SYNC, K_SPARE_REFILL_AGE, K_SPARE_WORKLIST, K_STEP_PERSISTENT, K_STEP_WPC, K_WPC, K_COUNT };
+static const char* const g_knob_names[K_COUNT] = {"SPL_STEP_PAIRED", "SPL_DEAL_BATCH", "SPL_DEAL_MAX_OUTPUTS", "SPL_ROLLOUT_CHUNK", "SPL_ROLLOUT_CTAS_PER_SM", "SPL_ROLLOUT_SYNC", "SPL_SPARE_REFILL_AGE", "SPL_SPARE_WORKLIST", "SPL_STEP_PERSISTENT", "SPL_STEP_WPC", "SPL_WPC"};
 static int g_knobs[K_COUNT];
 static bool g_knob_set[K_COUNT];
 static void load_knobs() {
@@ -1417,6 +1531,8 @@ int spl_init(void) {
 	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false, 4, SPL_OUT_COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<true, 4, SPL_OUT_F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	SPL_CUDA(cudaFuncSetAttribute(spl_step_kernel<false, 4, SPL_OUT_F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_paired_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	SPL_CUDA(cudaFuncSetAttribute(spl_step_paired_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	SPL_SETUP((spl_rollout_kernel<1>), 2, 0, 32)
 	SPL_SETUP((spl_rollout_kernel<4>), 2, 1, 128)
 #undef SPL_SETUP
@@ -1613,7 +1729,14 @@ static int launch_step(const spl_envs_t* e, const spl_step_io_t* io, bool do_ste
 	LaunchShape L = launch_shape(e->n, do_step ? 0 : 1);
 	const bool timed = do_step && g_timing && g_ev_used < SPL_TIMING_POOL;
 	if (timed) SPL_CUDA(cudaEventRecord(g_ev[2 * g_ev_used], st));
-	if (f16) SPL_LAUNCH_STEP(SPL_OUT_F16)
+	const int64_t ntiles = (e->n + 31) / 32;
+	// two warps per tile (spl_step_paired_kernel) while every tile still fits the GPU in one wave of 4-tile CTAs, 4 per SM
+	const bool paired = !f16 && knob(K_STEP_PAIRED, 0) != 0 && (ntiles + SPL_PAIR_TILES - 1) / SPL_PAIR_TILES <= (int64_t)g_num_sms * 4;
+	if (paired) {
+		const unsigned grid = (unsigned)((ntiles + SPL_PAIR_TILES - 1) / SPL_PAIR_TILES);
+		if (do_step) spl_step_paired_kernel<true><<<grid, SPL_PAIR_TILES * 64, 0, st>>>(p);
+		else spl_step_paired_kernel<false><<<grid, SPL_PAIR_TILES * 64, 0, st>>>(p);
+	} else if (f16) SPL_LAUNCH_STEP(SPL_OUT_F16)
 	else SPL_LAUNCH_STEP(SPL_OUT_I32)
 	if (timed) SPL_CUDA(cudaEventRecord(g_ev[2 * g_ev_used++ + 1], st));
 	g_launches++;

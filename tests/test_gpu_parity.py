@@ -805,3 +805,34 @@ def test_replay_of_reference_autoreset_stream(VecEnv, how):
             if live[i]:
                 assert digest(o[i], m[i], rows[i], r[i], te[i], int(ib[i])) == g["digests"][t], (how, g["seed"], t)
     assert _np(env.episode).tolist() == [4] * n
+
+
+def test_paired_warp_step_kernel_is_bit_exact(VecEnv, oracle, monkeypatch):
+    """The experimental two-warps-per-tile single-step kernel (SPL_STEP_PAIRED=1: rules warpgroup + helper warpgroup with
+    setmaxnreg register hand-over) against the oracle: every output of every step, Philox and MT19937 decks, ragged size."""
+    monkeypatch.setenv("SPL_STEP_PAIRED", "1")
+    for shuffle, n in (("mt19937", 4096 + 33), ("philox", 1000)):
+        env = VecEnv(n, seed=31, shuffle=shuffle, autoreset=True)  # (spl_init re-reads the knobs)
+        obs, info = env.reset()
+        ref = oracle.OracleVec(n, seed_base=31)
+        if shuffle == "mt19937":
+            ref.reset()
+        else:
+            ref.import_rows(_np(env.export_state()))
+        actions = env.sample_random_actions().clone()
+        for t in range(90):
+            a = _np(actions).copy()
+            out = env.step(actions, sample_next=True)  # (Philox decks: the oracle is handed the GPU's state of every re-dealt game)
+            if shuffle == "mt19937":
+                assert_step_equal(env, out, tuple(x.copy() for x in ref.step(a, autoreset=True)), t, check_state=ref.export_rows())
+            else:
+                robs, rrew, rterm, rinfo, rmask = (x.copy() for x in ref.step(a, autoreset=False))
+                assert np.array_equal(_np(out[1]), rrew) and np.array_equal(_np(out[2]).astype(np.uint8), rterm), t
+                rows = _np(env.export_state())
+                done = rterm.astype(bool)
+                assert np.array_equal(rows[~done], ref.export_rows()[~done]), t
+                assert np.array_equal(_np(out[0])[~done], robs[~done]) and np.array_equal(_np(out[4]["action_mask"])[~done], rmask[~done]), t
+                ref.import_rows(rows, which=done.astype(np.uint8))
+            actions = env.next_action.clone()
+    monkeypatch.setenv("SPL_STEP_PAIRED", "0")
+    VecEnv(64, seed=1)  # restore the default knobs for the tests that follow
