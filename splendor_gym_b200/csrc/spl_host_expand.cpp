@@ -177,7 +177,7 @@ void spl_expand_block(const uint8_t* obs_lo, const uint32_t* side_lo, int64_t lo
 // calls spl_host_step back to back), then sleep on a condition variable.
 // ------------------------------------------------------------------------------------------------
 struct SplPool {
-	int threads = 0;  // including the caller (worker 0)
+	int threads = 0;  // dedicated workers; the caller only waits (and watches the stream for errors)
 	pthread_t tid[SPL_POOL_MAX];
 	int index[SPL_POOL_MAX];
 	std::atomic<uint64_t> generation{0};
@@ -239,14 +239,8 @@ static void run_share(SplHostJob* job, int j) {
 		const uint64_t want = job->tag_base + (uint64_t)r + 1u;
 		const uint64_t* flag = job->ring_flags + (size_t)j * job->ring_slots + (size_t)(r % job->ring_slots);
 		uint64_t f;
-		unsigned spins = 0;
 		while (((f = __atomic_load_n(flag, __ATOMIC_ACQUIRE)) & ~(1ull << 63)) != want) {
 			if (job->abort.load(std::memory_order_relaxed)) return;
-			// worker 0 is the thread that owns the CUDA context: it watches the stream for errors while it waits
-			if (j == 0 && job->poll && (++spins & 0x3FFFu) == 0 && job->poll(job->poll_ctx)) {
-				job->abort.store(1);
-				return;
-			}
 			cpu_relax();
 		}
 		if (r == 0) t_first = spl_now_us();
@@ -304,7 +298,7 @@ static void pool_shutdown() {
 	pthread_mutex_lock(&P->mu);
 	pthread_cond_broadcast(&P->cv);
 	pthread_mutex_unlock(&P->mu);
-	for (int j = 1; j < P->threads; j++) pthread_join(P->tid[j], nullptr);
+	for (int j = 0; j < P->threads; j++) pthread_join(P->tid[j], nullptr);
 	delete P;
 	g_pool = nullptr;
 }
@@ -334,8 +328,8 @@ static void choose_cpus(SplPool* P) {
 	int mine[1024];
 	const int per = rank_cpus(mine, 1024);
 	if (per == 0) return;
-	// worker 0 is the caller's thread and is left where the OS put it; workers 1.. take the rank's cores from the top
-	for (int j = 1; j < P->threads; j++) P->cpus[j] = mine[per - 1 - ((j - 1) % per)];
+	// workers take the rank's cores from the top; the caller's thread is left where the OS put it
+	for (int j = 0; j < P->threads; j++) P->cpus[j] = mine[per - 1 - (j % per)];
 }
 
 // Run the calling thread on the rank's cores while it allocates and first-touches buffers (several ranks per node only:
@@ -384,7 +378,7 @@ static SplPool* pool_get() {
 	P->threads = want > SPL_POOL_MAX ? SPL_POOL_MAX : want;
 	choose_cpus(P);
 	g_pool = P;
-	for (int j = 1; j < P->threads; j++) {
+	for (int j = 0; j < P->threads; j++) {
 		P->index[j] = j;
 		pthread_create(&P->tid[j], nullptr, worker_main, &P->index[j]);
 	}
@@ -399,13 +393,12 @@ static SplPool* pool_get() {
 SplHostJob* spl_pool_job() { return &pool_get()->job; }
 int spl_pool_threads() { return pool_get()->threads; }
 
-// run the job that was filled into spl_pool_job(): the caller works as worker 0 and returns when every share is done
-void spl_pool_run() {
-	SplPool* P = pool_get();
-	SplHostJob* job = &P->job;
-	if (job->threads > P->threads) job->threads = P->threads;
-	if (job->threads < 1) job->threads = 1;
-	job->abort.store(0);
+// Run the job that was filled into spl_pool_job() and return when every share is done.  The caller's thread does none of the
+// widening: it may be held up inside the kernel launch (a profiler serialising launches, a slow driver call) while the push
+// kernel already waits for ring slots to be emptied -- only threads that are free to run may own a share.  It waits for the
+// GPU-written share (after_wait) and watches the stream for errors.
+static void pool_dispatch(SplPool* P) {
+	P->job.abort.store(0);
 	P->done.store(0, std::memory_order_relaxed);
 	P->generation.fetch_add(1, std::memory_order_release);
 	if (P->sleepers.load() > 0) {
@@ -413,9 +406,20 @@ void spl_pool_run() {
 		pthread_cond_broadcast(&P->cv);
 		pthread_mutex_unlock(&P->mu);
 	}
-	run_share(job, 0);
+}
+
+void spl_pool_run() {
+	SplPool* P = pool_get();
+	SplHostJob* job = &P->job;
+	if (job->threads > P->threads) job->threads = P->threads;
+	if (job->threads < 1) job->threads = 1;
+	pool_dispatch(P);
 	if (job->after_share0) job->after_share0(job);
-	while (P->done.load(std::memory_order_acquire) < P->threads - 1) cpu_relax();
+	unsigned spins = 0;
+	while (P->done.load(std::memory_order_acquire) < P->threads) {
+		if (job->poll && (++spins & 0x3FFFu) == 0 && !job->abort.load(std::memory_order_relaxed) && job->poll(job->poll_ctx)) job->abort.store(1);
+		cpu_relax();
+	}
 }
 
 // streaming-store rate of the pool (GB/s written) over `bytes` per thread, `reps` passes: the ceiling the widened
@@ -481,19 +485,9 @@ extern "C" double spl_host_store_rate(int64_t bytes_per_thread, int reps, int mo
 
 void spl_pool_run_custom() {
 	SplPool* P = pool_get();
-	SplHostJob* job = &P->job;
-	// custom jobs run through the same generation hand-shake; run_share is bypassed by cpu_groups == 0
-	job->cpu_groups = 0;
-	job->abort.store(0);
-	P->done.store(0, std::memory_order_relaxed);
-	P->generation.fetch_add(1, std::memory_order_release);
-	if (P->sleepers.load() > 0) {
-		pthread_mutex_lock(&P->mu);
-		pthread_cond_broadcast(&P->cv);
-		pthread_mutex_unlock(&P->mu);
-	}
-	job->custom(job->custom_ctx, 0);
-	while (P->done.load(std::memory_order_acquire) < P->threads - 1) cpu_relax();
+	P->job.cpu_groups = 0;
+	pool_dispatch(P);
+	while (P->done.load(std::memory_order_acquire) < P->threads) cpu_relax();
 }
 
 void spl_parallel_copy(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
