@@ -410,6 +410,8 @@ static int host_run(spl_host_t* h, const spl_envs_t* envs, const spl_host_io_t* 
 	if (do_step && !io->actions) return SPL_E_BADARG;
 	const int64_t n = h->n;
 	const double t0 = spl_now_us();
+	spl_pool_threads();  // (creates the pool on first use)
+	SplCallerOffWorkers off_the_worker_cores;
 	spl_step_io_t dio;
 	memset(&dio, 0, sizeof(dio));
 	if (do_step) {
@@ -426,9 +428,6 @@ static int host_run(spl_host_t* h, const spl_envs_t* envs, const spl_host_io_t* 
 	dio.stats = io->stats;
 	dio.action_key = io->action_key, dio.action_t = io->action_t;
 	dio.autoreset = io->autoreset;
-	int rc = spl_launch_compact(envs, &dio, do_step, h->d_obs, h->d_side, st);
-	if (rc) return rc;
-
 	const bool want_obs = io->obs || io->obs_u8;
 	const bool direct_ok = resolve_direct(h, io);
 	PushParams p = h->seen_dev;
@@ -448,11 +447,6 @@ static int host_run(spl_host_t* h, const spl_envs_t* envs, const spl_host_io_t* 
 	if (T > p.cpu_groups) T = p.cpu_groups > 0 ? p.cpu_groups : 1;
 	p.threads = T;
 	for (int j = 0; j < T; j++) h->h_consumed[8 * j] = h->tag_base;  // every worker starts the lock-step with an empty ring
-	spl_push_kernel<<<h->push_ctas, h->push_threads, 0, st>>>(p);
-	g_launches++;
-	SPL_CUDA(cudaGetLastError());
-	const double t1 = spl_now_us();
-
 	SplHostJob* job = spl_pool_job();
 	*job = SplHostJob();
 	job->io = *io, job->n = n;
@@ -482,7 +476,22 @@ static int host_run(spl_host_t* h, const spl_envs_t* envs, const spl_host_io_t* 
 		}
 		hh->t_gpu = spl_now_us();
 	};
-	spl_pool_run();
+	// The workers are started BEFORE the kernels are launched: a launch that only returns when its kernel has finished
+	// (CUDA_LAUNCH_BLOCKING, a profiler serialising launches) must find somebody emptying the ring slots the push kernel
+	// waits for.  Until the first tag arrives they only poll.
+	spl_pool_start();
+	int rc = spl_launch_compact(envs, &dio, do_step, h->d_obs, h->d_side, st);
+	if (rc == 0) {
+		spl_push_kernel<<<h->push_ctas, h->push_threads, 0, st>>>(p);
+		g_launches++;
+		rc = (int)cudaGetLastError();
+	}
+	if (rc) {
+		spl_pool_abort();
+		return rc;
+	}
+	const double t1 = spl_now_us();
+	spl_pool_wait();
 	const double t3 = spl_now_us();
 	if (job->abort.load()) {
 		cudaError_t q = cudaStreamSynchronize(st);

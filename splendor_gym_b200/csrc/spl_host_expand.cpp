@@ -350,6 +350,24 @@ SplRankAffinity::~SplRankAffinity() {
 	if (active) sched_setaffinity(0, sizeof(saved), &saved);
 }
 
+// While a lock-step is in flight the pinned workers spin on their cores; the caller's thread still has kernels to launch and
+// must not be time-sliced against one of them (a runnable thread sharing a core with a spinning worker waits for a scheduler
+// tick: milliseconds).  For the duration of the call the caller is kept off the workers' cores; its mask is put back after.
+SplCallerOffWorkers::SplCallerOffWorkers() : active(false) {
+	SplPool* P = g_pool;
+	if (!g_pin || P == nullptr) return;
+	if (sched_getaffinity(0, sizeof(saved), &saved) != 0) return;
+	cpu_set_t set = saved;
+	int removed = 0;
+	for (int j = 0; j < P->threads; j++)
+		if (P->cpus[j] >= 0 && CPU_ISSET(P->cpus[j], &set)) CPU_CLR(P->cpus[j], &set), removed++;
+	if (removed == 0 || CPU_COUNT(&set) == 0) return;  // nothing pinned, or the workers own every core this thread may use
+	active = sched_setaffinity(0, sizeof(set), &set) == 0;
+}
+SplCallerOffWorkers::~SplCallerOffWorkers() {
+	if (active) sched_setaffinity(0, sizeof(saved), &saved);
+}
+
 // default size of the pool: 3/4 of the cores this rank may use.  Measured (16 vCPUs, tools/microbench/host_bw.c):
 // streaming stores peak at 8-12 threads (200 GB/s) and drop to 150 GB/s at 16.
 static void default_threads() {
@@ -408,18 +426,38 @@ static void pool_dispatch(SplPool* P) {
 	}
 }
 
-void spl_pool_run() {
+// Two halves: spl_pool_start() hands the job to the workers (they begin to poll their arrival tags), spl_pool_wait() returns
+// when every share is done.  spl_host_step starts the workers BEFORE it launches the kernels: a launch that blocks until the
+// kernel has finished (CUDA_LAUNCH_BLOCKING, a profiler serialising launches) would otherwise wait for ring slots that
+// nobody has been asked to empty yet.
+void spl_pool_start() {
 	SplPool* P = pool_get();
 	SplHostJob* job = &P->job;
 	if (job->threads > P->threads) job->threads = P->threads;
 	if (job->threads < 1) job->threads = 1;
 	pool_dispatch(P);
+}
+
+void spl_pool_wait() {
+	SplPool* P = pool_get();
+	SplHostJob* job = &P->job;
 	if (job->after_share0) job->after_share0(job);
 	unsigned spins = 0;
 	while (P->done.load(std::memory_order_acquire) < P->threads) {
 		if (job->poll && (++spins & 0x3FFFu) == 0 && !job->abort.load(std::memory_order_relaxed) && job->poll(job->poll_ctx)) job->abort.store(1);
 		cpu_relax();
 	}
+}
+
+void spl_pool_abort() {  // a launch failed after spl_pool_start: release the workers
+	SplPool* P = pool_get();
+	P->job.abort.store(1);
+	while (P->done.load(std::memory_order_acquire) < P->threads) cpu_relax();
+}
+
+void spl_pool_run() {
+	spl_pool_start();
+	spl_pool_wait();
 }
 
 // streaming-store rate of the pool (GB/s written) over `bytes` per thread, `reps` passes: the ceiling the widened

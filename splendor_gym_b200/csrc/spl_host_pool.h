@@ -64,10 +64,20 @@ struct SplRankAffinity {  // scope guard, see spl_host_expand.cpp
 	~SplRankAffinity();
 };
 
+struct SplCallerOffWorkers {  // scope guard, see spl_host_expand.cpp
+	cpu_set_t saved;
+	bool active;
+	SplCallerOffWorkers();
+	~SplCallerOffWorkers();
+};
+
 double spl_now_us();
 SplHostJob* spl_pool_job();
 int spl_pool_threads();
 void spl_pool_run();
+void spl_pool_start();
+void spl_pool_wait();
+void spl_pool_abort();
 void spl_pool_run_custom();
 void spl_job_share(const SplHostJob* job, int j, int64_t* start, int64_t* len);
 void spl_expand_block(const uint8_t* obs_lo, const uint32_t* side_lo, int64_t lo, int64_t hi, const spl_host_io_t* io);
