@@ -707,6 +707,10 @@ def run_b200(args):
                "host_bytes_written_per_step": out_bytes, "host_threads": host_threads,
                "host_written_gbs": written_gbs, "host_store_gbs": store_gbs, "host_fill_gbs": fill_gbs,
                "frac_of_host_ceiling": written_gbs / store_gbs if store_gbs > 0 else None,
+               # the memory system also carries the staging bytes (written by the link, read back by a worker) of the share the
+               # host widens: results + 2 x 181.5 B per such env-step -- the path's whole host-memory traffic against the same ceiling
+               "host_traffic_bytes_per_step": int(out_bytes + 2 * 181.5 * N * (1.0 - share)),
+               "frac_of_host_ceiling_all_traffic": (written_gbs * (out_bytes + 2 * 181.5 * N * (1.0 - share)) / out_bytes) / store_gbs if store_gbs > 0 else None,
                "host_ceiling": "spl_host_store_rate: the worker pool widening uint8 -> int32 with non-temporal stores into %d MB (mode 1; "
                                "host_fill_gbs = plain streaming fill), sustained over >= 40 ms, same threads and pinning as the path, summed over the "
                                "ranks of the node measuring concurrently" % (out_bytes >> 20),
