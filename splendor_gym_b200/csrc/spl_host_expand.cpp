@@ -357,10 +357,26 @@ SplCallerOffWorkers::SplCallerOffWorkers() : active(false) {
 	SplPool* P = g_pool;
 	if (!g_pin || P == nullptr) return;
 	if (sched_getaffinity(0, sizeof(saved), &saved) != 0) return;
-	cpu_set_t set = saved;
+	// several ranks per node: stay inside this rank's own slice (other ranks' workers spin on theirs); else anywhere but on a worker
+	cpu_set_t set;
+	const char* lws = getenv("LOCAL_WORLD_SIZE");
+	if (lws && atoi(lws) > 1) {
+		int mine[1024];
+		const int per = rank_cpus(mine, 1024);
+		CPU_ZERO(&set);
+		for (int k = 0; k < per; k++)
+			if (CPU_ISSET(mine[k], &saved)) CPU_SET(mine[k], &set);
+	} else {
+		set = saved;
+	}
 	int removed = 0;
 	for (int j = 0; j < P->threads; j++)
 		if (P->cpus[j] >= 0 && CPU_ISSET(P->cpus[j], &set)) CPU_CLR(P->cpus[j], &set), removed++;
+	if (CPU_COUNT(&set) == 0) {  // the workers own the whole slice: anywhere but on a worker of this rank
+		set = saved;
+		for (int j = 0; j < P->threads; j++)
+			if (P->cpus[j] >= 0) CPU_CLR(P->cpus[j], &set);
+	}
 	if (removed == 0 || CPU_COUNT(&set) == 0) return;  // nothing pinned, or the workers own every core this thread may use
 	active = sched_setaffinity(0, sizeof(set), &set) == 0;
 }
