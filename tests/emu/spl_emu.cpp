@@ -97,6 +97,9 @@ void emu_env_step(const int32_t* row, int32_t action, int32_t* row_out, int32_t*
 	spl_export_row(s, deck, row_out);
 }
 
+// spl_import_state's admission rule for a flat row
+int emu_row_valid(const int32_t* row) { return spl_row_valid(row) ? 1 : 0; }
+
 // rollout work-unit chunking: chunk c of a `steps`-step rollout -> [start, start + len)
 int emu_chunk_bounds(int c, int steps, int chunk, int* start, int* len) { return spl_chunk_bounds(c, steps, chunk, *start, *len) ? 1 : 0; }
 int emu_num_chunks(int steps, int chunk) { return spl_num_chunks(steps, chunk); }

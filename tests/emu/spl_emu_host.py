@@ -87,3 +87,8 @@ def chunks(steps, chunk):
         c += 1
     assert L.emu_num_chunks(steps, chunk) == c
     return out
+
+
+def row_valid(row) -> bool:
+    r = np.ascontiguousarray(row, np.int32)
+    return bool(lib().emu_row_valid(_p(r, C.c_int32)))

@@ -139,3 +139,27 @@ def test_rollout_chunking_partitions_the_steps():
             assert all(n <= 2 * chunk for _, n in ch)
             assert ch[-1][1] <= 3  # short last unit -> short tail of the launch
             assert len(ch) <= steps // chunk + 8
+
+
+def test_row_validation_accepts_every_reference_row_and_rejects_what_would_be_truncated():
+    """spl_row_valid (the admission rule of spl_import_state): every row the reference produced -- initial states, the hand-built
+    edge cases of its own tests, the wrapper / auto-reset fixtures -- is inside the packed state's domain; rows whose counters
+    would not fit the byte-wise arithmetic (>= 128), whose ids fall outside the card / noble tables or whose lists are too long
+    are rejected instead of being masked to a byte."""
+    from conftest import load_golden
+    import spl_emu_host as E
+
+    rows = [np.array(c["row_in"], np.int32) for c in load_golden("edge_cases.json") if "row_in" in c]
+    rows += [np.array(g["row0"], np.int32) for g in load_golden("wrappers.json")]
+    rows += [np.array(r, np.int32) for g in load_golden("autoreset_stream.json") for r in g["starts"]]
+    rows += [np.array(p["row"], np.int32) for p in load_golden("logger_strings.json")]
+    assert len(rows) > 100 and all(E.row_valid(r) for r in rows)
+    base = rows[-1]
+    for col, val in ((0, 128), (0, -1), (6, 200), (17, 128), (18, 4), (52, 90), (52, -2), (64, 41), (65, 31), (66, 21), (67, 10),
+                     (70, 2), (71, 256), (74, 2), (76, 90)):
+        bad = base.copy()
+        bad[col] = val
+        assert not E.row_valid(bad), (col, val)
+    ok = base.copy()
+    ok[0], ok[17], ok[71] = 127, 127, 255  # the largest admissible counters
+    assert E.row_valid(ok)

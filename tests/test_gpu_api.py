@@ -624,3 +624,24 @@ def test_ppo_rollout_f16_policy_input_matches_cast_path():
     assert buf["obs"].dtype == torch.uint8
     legal = buf["masks"].gather(2, buf["actions"].long().unsqueeze(2)).squeeze(2)
     assert bool((legal[buf["masks"].sum(dim=2) > 0] == 1).all()) and int(buf["terminals"].sum()) > 50
+
+
+@pytest.mark.gpu
+def test_import_state_rejects_rows_outside_the_domain():
+    """spl_import_state validates instead of truncating: a row with a counter >= 128 or a card id >= 90 is not imported (its env
+    keeps its state), the valid rows of the same call are, and the call reports SPL_E_BADROW."""
+    from splendor_gym_b200 import SplendorVecEnv
+    from splendor_gym_b200._lib import SplendorB200Error
+
+    env = SplendorVecEnv(8, seed=4, shuffle="mt19937", autoreset=False)
+    env.reset()
+    before = env.export_state().clone()
+    rows = before.clone()
+    rows[1, 0] = 200      # bank white = 200 would not fit the byte-wise arithmetic
+    rows[5, 52] = 97      # board slot holds a card id outside the 90-card table
+    rows[2, 0] = 3        # a valid edit
+    with pytest.raises(SplendorB200Error, match="outside the engine's domain"):
+        env.import_state(rows)
+    after = env.export_state()
+    assert torch.equal(after[1], before[1]) and torch.equal(after[5], before[5])
+    assert int(after[2, 0]) == 3 and torch.equal(after[[0, 3, 4, 6, 7]], before[[0, 3, 4, 6, 7]])
