@@ -290,7 +290,7 @@ int spl_host_observe(spl_host_t *h, const spl_envs_t *envs, const spl_host_io_t 
  * (word 0 = mask bits 0-31; word 1 = mask bits 32-44 | reward code << 16 | terminated << 24; word 2 = info |
  * next action << 8) in HOST memory -> the non-NULL host arrays of `io`.  Pure CPU; needs no device. */
 int spl_host_expand(const uint8_t *obs_u8, const void *side, int64_t n, const spl_host_io_t *io);
-/* host threads used for widening (n <= 0: query; default 3/4 of the cores this rank may run on, SPL_HOST_THREADS
+/* host threads used for widening (n <= 0: query; default: the cores this rank may run on minus two, at least 3/4 of them; SPL_HOST_THREADS
  * overrides); returns the count.  Workers are pinned to distinct cores unless spl_host_set_pinning(0). */
 int spl_host_set_threads(int n);
 int spl_host_set_pinning(int on);

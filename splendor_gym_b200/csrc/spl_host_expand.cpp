@@ -384,8 +384,9 @@ SplCallerOffWorkers::~SplCallerOffWorkers() {
 	if (active) sched_setaffinity(0, sizeof(saved), &saved);
 }
 
-// default size of the pool: 3/4 of the cores this rank may use.  Measured (16 vCPUs, tools/microbench/host_bw.c):
-// streaming stores peak at 8-12 threads (200 GB/s) and drop to 150 GB/s at 16.
+// default size of the pool: the cores this rank may use minus two (one for the caller's thread, which launches the kernels and
+// then only waits, one for everything else in the process), at least 3/4 of them.  Measured on a 16-vCPU box with the final
+// path (tools/sweep_host.py, same box): 10 workers 811 us per lock-step, 12: 753-823, 13: 742, 14: 704, 15: 730.
 static void default_threads() {
 	cpu_set_t set;
 	int n = 0;
@@ -393,7 +394,7 @@ static void default_threads() {
 	if (n < 1) n = 1;
 	const char* lws = getenv("LOCAL_WORLD_SIZE");  // one process per GPU (torchrun): the ranks of a node share its cores
 	if (lws && atoi(lws) > 1) n /= atoi(lws);
-	n = (n * 3 + 3) / 4;
+	n = n - 2 > (n * 3 + 3) / 4 ? n - 2 : (n * 3 + 3) / 4;
 	const char* e = getenv("SPL_HOST_THREADS");
 	if (e && atoi(e) > 0) n = atoi(e);
 	if (n < 1) n = 1;

@@ -113,7 +113,7 @@ print(json.dumps({"threads": threads, "ok": ok, "rate_positive": rate > 0, "core
 
 def test_host_pool_under_two_local_ranks(tmp_path):
     """The host half of the host-buffer path (worker pool, per-rank core slices, widening) with two ranks of one node running at
-    the same time: each rank sizes its pool from its share of the cores (3/4 of cores / LOCAL_WORLD_SIZE), pins its workers
+    the same time: each rank sizes its pool from its share of the cores (cores / LOCAL_WORLD_SIZE minus two, at least 3/4 of them), pins its workers
     inside its own slice and widens correctly; the caller's affinity mask is left as it was."""
     script = tmp_path / "host_worker.py"
     script.write_text(HOST_WORKER % {"root": ROOT})
@@ -128,5 +128,6 @@ def test_host_pool_under_two_local_ranks(tmp_path):
         assert p.returncode == 0, err[-2000:]
         rec = json.loads(out.strip().splitlines()[-1])
         assert rec["ok"] and rec["rate_positive"]
-        assert rec["threads"] == max(1, min(32, ((cores // 2) * 3 + 3) // 4))
+        per = max(1, cores // 2)
+        assert rec["threads"] == max(1, min(32, max(per - 2, (per * 3 + 3) // 4)))
         assert rec["cores"] == cores  # the calling thread's mask is restored after the rank-local first touch
