@@ -258,9 +258,9 @@ SPL_HD uint32_t spl_take3_combo(uint32_t a) { return (uint32_t)(SPL_TAKE3_COMBOS
 // ------------------------------------------------------------------------------------------------
 // legal_moves (engine/rules.py:40-93) as a 45-bit set for the player to move
 // ------------------------------------------------------------------------------------------------
-// The 15 card slots (12 board + my 3 reserved) are evaluated one at a time so that a caller can interleave them with
-// other work (the step kernels run them inside the observation-tile store loop, where the warp otherwise only waits
-// for the store queue); spl_legal_mask below is the plain sequence.
+// The 15 card slots (12 board + my 3 reserved) can be evaluated one at a time (begin / slot / finish), so that a caller may
+// interleave them with other work; spl_legal_mask below is the plain sequence every kernel uses today.  (Round 2 ran the
+// slots inside the observation-tile store loop of the step kernels: no gain)
 struct SplMaskBuilder {
 	uint32_t wealth, gold, afford, present;
 	SPL_HD_MEMBER void begin(const SplState& s) {
